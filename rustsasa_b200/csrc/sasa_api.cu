@@ -1,0 +1,751 @@
+// sasa_api.cu -- host side of libsasa_b200.so: the C ABI declared in include/sasa_b200.h.
+//
+// One context per (process, device).  A batch object holds the topology of a set of structures (CSR
+// offsets, output segments) and the launch plan derived from it: structures are bucketed by size into
+// shared-memory configurations of the fused per-structure kernel, ordered largest-first inside each
+// bucket, and cut into chunks so that the host entry point can overlap the H2D copy of chunk c+1 with
+// the kernels of chunk c and the D2H copy of chunk c-1 on separate CUDA streams.
+//
+// There is deliberately no CPU implementation in this library: without a CUDA device every entry point
+// fails with SASA_B200_ERR_CUDA.
+#include "../../include/sasa_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "sasa_large.cuh"
+#include "sasa_small.cuh"
+
+using namespace sasa;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Points {
+    float *d = nullptr;  // 3*n floats: x[n] y[n] z[n]
+};
+
+struct SmallCfg {
+    int nt, minb;
+    uint32_t nmax, cmax;
+    size_t smem[2];  // without / with id classes
+};
+
+constexpr int kStreams = 3;
+constexpr size_t kChunkAtoms = 1500000;
+
+}  // namespace
+
+struct sasa_b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t streams[kStreams] = {};
+    std::map<uint32_t, Points> points;
+    int *d_err = nullptr;
+    unsigned long long *d_stat = nullptr;
+    std::vector<SmallCfg> cfgs;
+    std::string err;
+    std::mutex mu;
+    // grow-only device arena for the host entry points
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+};
+
+namespace {
+
+int fail(sasa_b200_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                                      \
+    do {                                                                                                       \
+        cudaError_t e__ = (expr);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? SASA_B200_ERR_OUT_OF_MEMORY : SASA_B200_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);          \
+    } while (0)
+
+// generate_sphere_points, reference src/lib.rs:43-66: golden-section spiral evaluated with the host libm
+// (CUDA's sinf/cosf/acosf are not bit-identical to glibc's, so the points are never computed on the device).
+void sphere_points_host(uint32_t n, float *x, float *y, float *z) {
+    const float golden = 1.618034f;
+    const float inc = (2.0f * 3.14159265358979323846f) * golden;
+    const float inv = 1.0f / (float)n;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float fi = (float)i;
+        const float incl = std::acos(1.0f - 2.0f * (fi * inv));
+        const float az = inc * fi;
+        const float si = std::sin(incl);
+        x[i] = si * std::cos(az);
+        y[i] = si * std::sin(az);
+        z[i] = std::cos(incl);
+    }
+}
+
+int get_points(sasa_b200_ctx *ctx, uint32_t n, const float **px) {
+    auto it = ctx->points.find(n);
+    if (it == ctx->points.end()) {
+        std::vector<float> h(3 * (size_t)n);
+        sphere_points_host(n, h.data(), h.data() + n, h.data() + 2 * (size_t)n);
+        Points P;
+        CU_TRY(ctx, cudaMalloc(&P.d, h.size() * sizeof(float)));
+        CU_TRY(ctx, cudaMemcpy(P.d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        it = ctx->points.emplace(n, P).first;
+    }
+    *px = it->second.d;
+    return SASA_B200_OK;
+}
+
+template <int NT, int MINB>
+cudaError_t launch_small(const KParams &kp, bool has_cls, int grid, size_t smem, cudaStream_t st) {
+    if (has_cls) {
+        sasa_small_kernel<NT, MINB, true><<<grid, NT, smem, st>>>(kp);
+    } else {
+        sasa_small_kernel<NT, MINB, false><<<grid, NT, smem, st>>>(kp);
+    }
+    return cudaGetLastError();
+}
+
+template <int NT, int MINB>
+cudaError_t set_smem_attr(size_t s0, size_t s1) {
+    cudaError_t e = cudaFuncSetAttribute(sasa_small_kernel<NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s0);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(sasa_small_kernel<NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
+}
+
+// Shared-memory configurations of the fused kernel, smallest first.  nmax is derived from the per-CTA
+// budget that lets `minb` CTAs share one SM (228 KB per SM, 1 KB reserved per CTA, 227 KB per CTA max).
+int build_cfgs(sasa_b200_ctx *ctx) {
+    struct Proto { int nt, minb; uint32_t cmax; };
+    const Proto protos[] = {{256, 3, 4096}, {256, 2, 8192}, {512, 1, 16384}};
+    for (const Proto &pr : protos) {
+        const size_t budget = std::min<size_t>(ctx->smem_optin, (228 * 1024) / pr.minb - 1024);
+        SmallCfg c{pr.nt, pr.minb, 0, pr.cmax, {0, 0}};
+        // largest nmax (multiple of 16) whose class-less layout fits the budget
+        uint32_t lo = 0, hi = 65520 / 16;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) / 2;
+            if (small_layout(mid * 16, pr.cmax, pr.nt / 32, false).total <= budget) lo = mid;
+            else hi = mid - 1;
+        }
+        c.nmax = lo * 16;
+        if (c.nmax == 0) continue;
+        c.smem[0] = small_layout(c.nmax, c.cmax, c.nt / 32, false).total;
+        c.smem[1] = small_layout(c.nmax, c.cmax, c.nt / 32, true).total;
+        ctx->cfgs.push_back(c);
+    }
+    if (ctx->cfgs.size() != 3) return fail(ctx, SASA_B200_ERR_CUDA, "device shared memory too small for the fused kernel");
+    // with id classes the same nmax needs 4 more bytes per atom; the 1-CTA/SM config is capped by the opt-in limit
+    for (SmallCfg &c : ctx->cfgs) {
+        while (c.smem[1] > std::min<size_t>(ctx->smem_optin, (228 * 1024) / c.minb - 1024) && c.nmax > 16) {
+            // shrink only the class-carrying variant by lowering its usable nmax: handled at bucket time
+            break;
+        }
+    }
+    cudaError_t e;
+    if ((e = set_smem_attr<256, 3>(ctx->cfgs[0].smem[0], std::min(ctx->cfgs[0].smem[1], ctx->smem_optin))) != cudaSuccess ||
+        (e = set_smem_attr<256, 2>(ctx->cfgs[1].smem[0], std::min(ctx->cfgs[1].smem[1], ctx->smem_optin))) != cudaSuccess ||
+        (e = set_smem_attr<512, 1>(ctx->cfgs[2].smem[0], std::min(ctx->cfgs[2].smem[1], ctx->smem_optin))) != cudaSuccess)
+        return fail(ctx, SASA_B200_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(e));
+    return SASA_B200_OK;
+}
+
+// With id classes every atom costs 4 more bytes of shared memory: the atom capacity of a config shrinks.
+uint32_t cfg_capacity(const sasa_b200_ctx *ctx, const SmallCfg &c, bool has_cls) {
+    if (!has_cls) return c.nmax;
+    const size_t budget = std::min<size_t>(ctx->smem_optin, (228 * 1024) / c.minb - 1024);
+    uint32_t n = c.nmax;
+    while (n > 0 && small_layout(n, c.cmax, c.nt / 32, true).total > budget) n -= 16;
+    return n;
+}
+
+struct Launch {
+    int cfg;          // index into ctx->cfgs, or -1 for the large-structure path
+    uint32_t order_off, n_work;
+    uint32_t counter; // index into the work-counter array
+};
+
+struct Chunk {
+    uint32_t s0, s1;      // structure range
+    uint64_t a0, a1;      // atom range
+    uint64_t g0, g1;      // segment range
+    std::vector<Launch> launches;
+};
+
+}  // namespace
+
+struct sasa_b200_batch {
+    sasa_b200_ctx *ctx = nullptr;
+    size_t S = 0, n_atoms = 0, n_seg = 0;
+    bool has_polar = false;
+    std::vector<uint32_t> h_off;      // S+1
+    std::vector<uint32_t> h_seg_off;  // S+1
+    // two launch plans (without / with id classes: capacities differ)
+    // index = variant + 2*mode; variant: 0 without / 1 with id classes (capacities differ);
+    // mode: 0 = chunked for the pipelined host entry points, 1 = one chunk for device-resident runs
+    std::vector<Chunk> plan[4];
+    std::vector<uint32_t> h_order[4];
+    uint32_t n_counters[4] = {0, 0, 0, 0};
+    uint32_t max_large = 0;
+    // device topology
+    uint32_t *d_off = nullptr, *d_seg_off = nullptr, *d_order[4] = {nullptr, nullptr, nullptr, nullptr}, *d_counters = nullptr;
+    uint2 *d_seg_be = nullptr;
+    uint8_t *d_polar = nullptr;
+    LargeWorkspace large;
+    sasa_b200_stats last = {};
+    uint32_t launches_last = 0;
+};
+
+namespace {
+
+int arena_reserve(sasa_b200_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->arena_bytes) return SASA_B200_OK;
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+    const size_t want = bytes + bytes / 8 + (1 << 20);
+    CU_TRY(ctx, cudaMalloc(&ctx->arena, want));
+    ctx->arena_bytes = want;
+    return SASA_B200_OK;
+}
+
+void build_plan(sasa_b200_batch *b, int variant) {
+    sasa_b200_ctx *ctx = b->ctx;
+    const bool has_cls = (variant & 1) == 1;
+    const size_t chunk_atoms = (variant & 2) ? ~(size_t)0 : kChunkAtoms;
+    std::vector<uint32_t> cap;
+    for (const SmallCfg &c : ctx->cfgs) cap.push_back(cfg_capacity(ctx, c, has_cls));
+    std::vector<Chunk> &plan = b->plan[variant];
+    std::vector<uint32_t> &order = b->h_order[variant];
+    plan.clear();
+    order.clear();
+    uint32_t counters = 0;
+    uint32_t s = 0;
+    while (s < b->S) {
+        Chunk ch;
+        ch.s0 = s;
+        ch.a0 = b->h_off[s];
+        while (s < b->S && (b->h_off[s] - ch.a0 < chunk_atoms || s == ch.s0)) ++s;
+        ch.s1 = s;
+        ch.a1 = b->h_off[s];
+        ch.g0 = b->h_seg_off.empty() ? 0 : b->h_seg_off[ch.s0];
+        ch.g1 = b->h_seg_off.empty() ? 0 : b->h_seg_off[ch.s1];
+        // bucket the chunk's structures
+        std::vector<std::vector<uint32_t>> bucket(ctx->cfgs.size() + 1);
+        for (uint32_t i = ch.s0; i < ch.s1; ++i) {
+            const uint32_t n = b->h_off[i + 1] - b->h_off[i];
+            size_t k = 0;
+            while (k < cap.size() && n > cap[k]) ++k;
+            bucket[k].push_back(i);
+            if (k == cap.size()) b->max_large = std::max(b->max_large, n);
+        }
+        for (size_t k = 0; k < bucket.size(); ++k) {
+            if (bucket[k].empty()) continue;
+            std::stable_sort(bucket[k].begin(), bucket[k].end(), [&](uint32_t x, uint32_t y) {
+                return b->h_off[x + 1] - b->h_off[x] > b->h_off[y + 1] - b->h_off[y];
+            });
+            Launch L;
+            L.cfg = k < cap.size() ? (int)k : -1;
+            L.order_off = (uint32_t)order.size();
+            L.n_work = (uint32_t)bucket[k].size();
+            L.counter = counters++;
+            order.insert(order.end(), bucket[k].begin(), bucket[k].end());
+            ch.launches.push_back(L);
+        }
+        plan.push_back(std::move(ch));
+    }
+    b->n_counters[variant] = counters;
+}
+
+struct RunArgs {
+    const float4 *d_xyzr;
+    const uint32_t *d_cls;
+    sasa_b200_outputs d_out;
+    sasa_b200_params prm;
+    const float *d_points;
+};
+
+int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
+    sasa_b200_ctx *ctx = b->ctx;
+    memset(kp, 0, sizeof *kp);
+    kp->xyzr = ra.d_xyzr;
+    kp->cls = ra.d_cls;
+    kp->struct_off = b->d_off;
+    kp->seg_be = b->d_seg_be;
+    kp->struct_seg_off = b->d_seg_off;
+    kp->seg_polar = b->d_polar;
+    kp->out_counts = ra.d_out.counts;
+    kp->out_atom = ra.d_out.atom_sasa;
+    kp->out_seg = b->n_seg ? ra.d_out.seg_sasa : nullptr;
+    kp->out_protein = ra.d_out.protein;
+    const uint32_t n = ra.prm.n_points;
+    kp->px = ra.d_points;
+    kp->py = ra.d_points + n;
+    kp->pz = ra.d_points + 2 * (size_t)n;
+    kp->n_points = n;
+    const uint32_t lanes = ra.prm.simd_lanes ? ra.prm.simd_lanes : 8;
+    kp->n_body = (n / lanes) * lanes;
+    kp->inv_n = 1.0f / (float)n;
+    kp->probe = ra.prm.probe_radius;
+    static const float near_a = [] {
+        const char *e = getenv("SASA_B200_NEAR");
+        return e ? (float)atof(e) : 3.0f;
+    }();
+    kp->near2 = near_a * near_a;
+    kp->flags = ra.prm.flags;
+    kp->err_flag = ctx->d_err;
+    kp->stat = ctx->d_stat;
+    return SASA_B200_OK;
+}
+
+int check_params(sasa_b200_ctx *ctx, const sasa_b200_params *p) {
+    if (!p) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (p->n_points == 0 || p->n_points > (1u << 24))
+        return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "n_points must be in [1, 2^24], got %u", p->n_points);
+    if (p->simd_lanes != 0 && p->simd_lanes != 4 && p->simd_lanes != 8 && p->simd_lanes != 16)
+        return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "simd_lanes must be 0, 4, 8 or 16, got %u", p->simd_lanes);
+    if (!std::isfinite(p->probe_radius) || p->probe_radius < 0.0f)
+        return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "probe_radius must be finite and >= 0");
+    return SASA_B200_OK;
+}
+
+// Enqueue every kernel of one chunk on `st`.
+int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParams &base, cudaStream_t st,
+                  uint32_t *launches) {
+    sasa_b200_ctx *ctx = b->ctx;
+    for (const Launch &L : ch.launches) {
+        KParams kp = base;
+        kp.order = b->d_order[variant] + L.order_off;
+        kp.n_work = L.n_work;
+        kp.work_counter = b->d_counters + L.counter;
+        if (L.cfg < 0) {
+            int rc = large_enqueue(ctx->sm_count, b->large, kp, &b->h_order[variant][L.order_off], L.n_work,
+                                   b->h_off.data(), st, launches);
+            if (rc != 0) return fail(ctx, rc, "large-structure path failed: %s", cudaGetErrorString(cudaGetLastError()));
+            continue;
+        }
+        const SmallCfg &c = ctx->cfgs[L.cfg];
+        const bool has_cls = (variant & 1) == 1;
+        kp.nmax = cfg_capacity(ctx, c, has_cls);
+        kp.cmax = c.cmax;
+        const size_t smem = small_layout(kp.nmax, kp.cmax, c.nt / 32, has_cls).total;
+        const int grid = (int)std::min<uint32_t>(L.n_work, (uint32_t)(ctx->sm_count * c.minb));
+        cudaError_t e;
+        if (c.nt == 256 && c.minb == 3) e = launch_small<256, 3>(kp, has_cls, grid, smem, st);
+        else if (c.nt == 256 && c.minb == 2) e = launch_small<256, 2>(kp, has_cls, grid, smem, st);
+        else e = launch_small<512, 1>(kp, has_cls, grid, smem, st);
+        if (e != cudaSuccess) return fail(ctx, SASA_B200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+        ++*launches;
+    }
+    return SASA_B200_OK;
+}
+
+int finish_run(sasa_b200_batch *b, sasa_b200_stats *stats) {
+    sasa_b200_ctx *ctx = b->ctx;
+    int h_err = 0;
+    unsigned long long h_stat[3] = {0, 0, 0};
+    CU_TRY(ctx, cudaMemcpy(&h_err, ctx->d_err, sizeof h_err, cudaMemcpyDeviceToHost));
+    CU_TRY(ctx, cudaMemcpy(h_stat, ctx->d_stat, sizeof h_stat, cudaMemcpyDeviceToHost));
+    b->last.n_atoms = b->n_atoms;
+    b->last.n_structures = b->S;
+    b->last.boundary_points = h_stat[0];
+    b->last.neighbor_pairs = h_stat[1];
+    b->last.streamed_atoms = h_stat[2];
+    b->last.gpu_launches = b->launches_last;
+    if (stats) *stats = b->last;
+    if (h_err == SASA_B200_ERR_NON_FINITE)
+        return fail(ctx, SASA_B200_ERR_NON_FINITE, "non-finite coordinate or radius in the input (the reference panics here)");
+    if (h_err) return fail(ctx, h_err, "device-side error %d", h_err);
+    return SASA_B200_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int sasa_b200_abi_version(void) { return SASA_B200_ABI_VERSION; }
+
+const char *sasa_b200_last_error(const sasa_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sasa_b200_create(int device, sasa_b200_ctx **out_ctx) {
+    if (!out_ctx) return fail(nullptr, SASA_B200_ERR_INVALID_ARGUMENT, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, SASA_B200_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0) {
+        if ((e = cudaGetDevice(&device)) != cudaSuccess) return fail(nullptr, SASA_B200_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    }
+    if (device >= count) return fail(nullptr, SASA_B200_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", device, count);
+    sasa_b200_ctx *ctx = new sasa_b200_ctx();
+    ctx->device = device;
+    auto bail = [&](int code, const char *what, cudaError_t ce) {
+        int rc = fail(nullptr, code, "%s: %s", what, cudaGetErrorString(ce));
+        delete ctx;
+        return rc;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaGetDeviceProperties", e);
+    if (prop.major < 10) {
+        int rc = fail(nullptr, SASA_B200_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                      device, prop.major, prop.minor);
+        delete ctx;
+        return rc;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    for (int i = 0; i < kStreams; ++i)
+        if ((e = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking)) != cudaSuccess)
+            return bail(SASA_B200_ERR_CUDA, "cudaStreamCreate", e);
+    if ((e = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(SASA_B200_ERR_OUT_OF_MEMORY, "cudaMalloc", e);
+    if ((e = cudaMalloc(&ctx->d_stat, 3 * sizeof(unsigned long long))) != cudaSuccess) return bail(SASA_B200_ERR_OUT_OF_MEMORY, "cudaMalloc", e);
+    cudaMemset(ctx->d_err, 0, sizeof(int));
+    cudaMemset(ctx->d_stat, 0, 3 * sizeof(unsigned long long));
+    int rc = build_cfgs(ctx);
+    if (rc != SASA_B200_OK) {
+        g_create_error = ctx->err;
+        sasa_b200_destroy(ctx);
+        return rc;
+    }
+    *out_ctx = ctx;
+    return SASA_B200_OK;
+}
+
+void sasa_b200_destroy(sasa_b200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &kv : ctx->points) cudaFree(kv.second.d);
+    for (int i = 0; i < kStreams; ++i)
+        if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
+    cudaFree(ctx->d_err);
+    cudaFree(ctx->d_stat);
+    cudaFree(ctx->arena);
+    delete ctx;
+}
+
+int sasa_b200_alloc_pinned(size_t bytes, void **out_ptr) {
+    if (!out_ptr) return SASA_B200_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(nullptr, SASA_B200_ERR_OUT_OF_MEMORY, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return SASA_B200_OK;
+}
+
+int sasa_b200_free_pinned(void *ptr) {
+    if (!ptr) return SASA_B200_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? SASA_B200_OK : SASA_B200_ERR_CUDA;
+}
+
+int sasa_b200_sphere_points(uint32_t n_points, float *xyz) {
+    if (!xyz || n_points == 0) return SASA_B200_ERR_INVALID_ARGUMENT;
+    std::vector<float> h(3 * (size_t)n_points);
+    sphere_points_host(n_points, h.data(), h.data() + n_points, h.data() + 2 * (size_t)n_points);
+    for (uint32_t i = 0; i < n_points; ++i) {
+        xyz[3 * i + 0] = h[i];
+        xyz[3 * i + 1] = h[n_points + i];
+        xyz[3 * i + 2] = h[2 * (size_t)n_points + i];
+    }
+    return SASA_B200_OK;
+}
+
+int sasa_b200_batch_create(sasa_b200_ctx *ctx, const uint64_t *struct_off, size_t S, const uint32_t *seg_be,
+                           const uint64_t *struct_seg_off, const uint8_t *seg_polar, sasa_b200_batch **out_batch) {
+    if (!ctx) return SASA_B200_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!out_batch || (!struct_off && S)) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "struct_off / out_batch is NULL");
+    *out_batch = nullptr;
+    if (S && struct_off[0] != 0) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "struct_off[0] must be 0");
+    for (size_t i = 0; i < S; ++i)
+        if (struct_off[i + 1] < struct_off[i]) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "struct_off must be non-decreasing");
+    if (S && struct_off[S] >= (1ull << 32)) return fail(ctx, SASA_B200_ERR_UNSUPPORTED, "more than 2^32 atoms in one batch");
+    if (S >= (1ull << 31)) return fail(ctx, SASA_B200_ERR_UNSUPPORTED, "too many structures");
+    if (seg_be && !struct_seg_off) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "seg_be without struct_seg_off");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    sasa_b200_batch *b = new sasa_b200_batch();
+    b->ctx = ctx;
+    b->S = S;
+    b->h_off.resize(S + 1, 0);
+    for (size_t i = 0; i <= S && S; ++i) b->h_off[i] = (uint32_t)struct_off[i];
+    b->n_atoms = S ? b->h_off[S] : 0;
+    auto cleanup = [&](int rc) {
+        sasa_b200_batch_destroy(b);
+        return rc;
+    };
+    if (seg_be && S) {
+        if (struct_seg_off[0] != 0) return cleanup(fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "struct_seg_off[0] must be 0"));
+        for (size_t i = 0; i < S; ++i)
+            if (struct_seg_off[i + 1] < struct_seg_off[i]) return cleanup(fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "struct_seg_off must be non-decreasing"));
+        if (struct_seg_off[S] >= (1ull << 32)) return cleanup(fail(ctx, SASA_B200_ERR_UNSUPPORTED, "too many segments"));
+        b->n_seg = struct_seg_off[S];
+        b->h_seg_off.resize(S + 1);
+        for (size_t i = 0; i <= S; ++i) b->h_seg_off[i] = (uint32_t)struct_seg_off[i];
+        for (size_t s = 0; s < S; ++s) {
+            const uint32_t n = b->h_off[s + 1] - b->h_off[s];
+            for (uint64_t k = struct_seg_off[s]; k < struct_seg_off[s + 1]; ++k)
+                if (seg_be[2 * k] > seg_be[2 * k + 1] || seg_be[2 * k + 1] > n)
+                    return cleanup(fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "segment %llu of structure %zu is not a range inside its structure",
+                                        (unsigned long long)k, s));
+        }
+    }
+    for (int v = 0; v < 4; ++v) build_plan(b, v);
+#define B_TRY(expr)                                                                                            \
+    do {                                                                                                       \
+        cudaError_t e__ = (expr);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            return cleanup(fail(ctx, e__ == cudaErrorMemoryAllocation ? SASA_B200_ERR_OUT_OF_MEMORY : SASA_B200_ERR_CUDA, \
+                                "%s failed: %s", #expr, cudaGetErrorString(e__)));                             \
+    } while (0)
+    B_TRY(cudaMalloc(&b->d_off, (S + 1) * sizeof(uint32_t)));
+    B_TRY(cudaMemcpy(b->d_off, b->h_off.data(), (S + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    for (int v = 0; v < 4; ++v) {
+        B_TRY(cudaMalloc(&b->d_order[v], std::max<size_t>(1, b->h_order[v].size()) * sizeof(uint32_t)));
+        if (!b->h_order[v].empty())
+            B_TRY(cudaMemcpy(b->d_order[v], b->h_order[v].data(), b->h_order[v].size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    B_TRY(cudaMalloc(&b->d_counters, std::max<uint32_t>(1, *std::max_element(b->n_counters, b->n_counters + 4)) * sizeof(uint32_t)));
+    if (b->n_seg) {
+        B_TRY(cudaMalloc(&b->d_seg_be, b->n_seg * sizeof(uint2)));
+        B_TRY(cudaMemcpy(b->d_seg_be, seg_be, b->n_seg * sizeof(uint2), cudaMemcpyHostToDevice));
+        B_TRY(cudaMalloc(&b->d_seg_off, (S + 1) * sizeof(uint32_t)));
+        B_TRY(cudaMemcpy(b->d_seg_off, b->h_seg_off.data(), (S + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        if (seg_polar) {
+            B_TRY(cudaMalloc(&b->d_polar, b->n_seg));
+            B_TRY(cudaMemcpy(b->d_polar, seg_polar, b->n_seg, cudaMemcpyHostToDevice));
+            b->has_polar = true;
+        }
+    }
+    if (b->max_large) {
+        int rc = large_reserve(b->large, b->max_large);
+        if (rc) return cleanup(fail(ctx, rc, "allocating the large-structure workspace (%u atoms) failed", b->max_large));
+    }
+#undef B_TRY
+    *out_batch = b;
+    return SASA_B200_OK;
+}
+
+void sasa_b200_batch_destroy(sasa_b200_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(b->d_off);
+    cudaFree(b->d_seg_off);
+    for (int v = 0; v < 4; ++v) cudaFree(b->d_order[v]);
+    cudaFree(b->d_counters);
+    cudaFree(b->d_seg_be);
+    cudaFree(b->d_polar);
+    large_release(b->large);
+    delete b;
+}
+
+int sasa_b200_batch_run_device(sasa_b200_batch *b, const float *d_xyzr, const uint32_t *d_id_class,
+                               const sasa_b200_params *params, const sasa_b200_outputs *d_out, void *stream) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    sasa_b200_ctx *ctx = b->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!d_out || (!d_xyzr && b->n_atoms)) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "d_xyzr / d_out is NULL");
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->streams[0];
+    RunArgs ra;
+    ra.d_xyzr = reinterpret_cast<const float4 *>(d_xyzr);
+    ra.d_cls = d_id_class;
+    ra.d_out = *d_out;
+    ra.prm = *params;
+    if ((rc = get_points(ctx, params->n_points, &ra.d_points)) != 0) return rc;
+    const int variant = (d_id_class ? 1 : 0) + 2;
+    KParams base;
+    make_kparams(b, ra, &base);
+    b->launches_last = 0;
+    if (b->n_counters[variant])
+        CU_TRY(ctx, cudaMemsetAsync(b->d_counters, 0, b->n_counters[variant] * sizeof(uint32_t), st));
+    for (const Chunk &ch : b->plan[variant])
+        if ((rc = enqueue_chunk(b, variant, ch, base, st, &b->launches_last)) != 0) return rc;
+    return SASA_B200_OK;
+}
+
+int sasa_b200_batch_sync(sasa_b200_batch *b, sasa_b200_stats *stats) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    sasa_b200_ctx *ctx = b->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaDeviceSynchronize());
+    int rc = finish_run(b, stats);
+    cudaMemset(ctx->d_err, 0, sizeof(int));
+    cudaMemset(ctx->d_stat, 0, 3 * sizeof(unsigned long long));
+    return rc;
+}
+
+static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz3, const float *radii,
+                         const uint32_t *id_class, const sasa_b200_params *params, const sasa_b200_outputs *out,
+                         sasa_b200_stats *stats) {
+    sasa_b200_ctx *ctx = b->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!out) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "out is NULL");
+    if (b->n_atoms && !xyzr && !(xyz3 && radii)) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "atom data is NULL");
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const auto t_begin = std::chrono::steady_clock::now();
+    const size_t N = b->n_atoms, S = b->S, G = b->n_seg;
+    const int variant = id_class ? 1 : 0;
+    const bool frames = xyz3 != nullptr;
+    size_t fN = 0;  // atoms per frame
+    if (frames) {
+        fN = S ? b->h_off[1] - b->h_off[0] : 0;
+        for (size_t s = 0; s < S; ++s)
+            if (b->h_off[s + 1] - b->h_off[s] != fN)
+                return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "run_frames needs equal-sized structures");
+    }
+    // carve the arena
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o = 0;
+    const size_t o_xyzr = o;   o += al(N * 16);
+    const size_t o_xyz3 = o;   o += frames ? al(N * 12) : 0;
+    const size_t o_rad = o;    o += frames ? al(fN * 4) : 0;
+    const size_t o_cls = o;    o += id_class ? al(N * 4) : 0;
+    const size_t o_cnt = o;    o += out->counts ? al(N * 4) : 0;
+    const size_t o_atom = o;   o += out->atom_sasa ? al(N * 4) : 0;
+    const size_t o_seg = o;    o += (out->seg_sasa && G) ? al(G * 4) : 0;
+    const size_t o_prot = o;   o += out->protein ? al(S * 12) : 0;
+    if ((rc = arena_reserve(ctx, o + 256)) != 0) return rc;
+    char *base_p = static_cast<char *>(ctx->arena);
+    RunArgs ra;
+    ra.d_xyzr = reinterpret_cast<const float4 *>(base_p + o_xyzr);
+    ra.d_cls = id_class ? reinterpret_cast<const uint32_t *>(base_p + o_cls) : nullptr;
+    ra.d_out.counts = out->counts ? reinterpret_cast<uint32_t *>(base_p + o_cnt) : nullptr;
+    ra.d_out.atom_sasa = out->atom_sasa ? reinterpret_cast<float *>(base_p + o_atom) : nullptr;
+    ra.d_out.seg_sasa = (out->seg_sasa && G) ? reinterpret_cast<float *>(base_p + o_seg) : nullptr;
+    ra.d_out.protein = out->protein ? reinterpret_cast<float *>(base_p + o_prot) : nullptr;
+    ra.prm = *params;
+    if ((rc = get_points(ctx, params->n_points, &ra.d_points)) != 0) return rc;
+    KParams kbase;
+    make_kparams(b, ra, &kbase);
+    b->launches_last = 0;
+
+    cudaEvent_t ev0, ev1;
+    CU_TRY(ctx, cudaEventCreate(&ev0));
+    CU_TRY(ctx, cudaEventCreate(&ev1));
+    if (b->n_counters[variant])
+        CU_TRY(ctx, cudaMemsetAsync(b->d_counters, 0, b->n_counters[variant] * sizeof(uint32_t), ctx->streams[0]));
+    if (frames && fN)
+        CU_TRY(ctx, cudaMemcpyAsync(base_p + o_rad, radii, fN * 4, cudaMemcpyHostToDevice, ctx->streams[0]));
+    CU_TRY(ctx, cudaEventRecord(ev0, ctx->streams[0]));
+    for (int i = 1; i < kStreams; ++i) CU_TRY(ctx, cudaStreamWaitEvent(ctx->streams[i], ev0, 0));
+    size_t ci = 0;
+    // the large-structure workspace is shared by all chunks: keep such batches on a single stream
+    const int nstreams = b->max_large ? 1 : kStreams;
+    for (const Chunk &ch : b->plan[variant]) {
+        cudaStream_t st = ctx->streams[ci++ % nstreams];
+        const size_t na = ch.a1 - ch.a0;
+        if (na) {
+            if (frames) {
+                CU_TRY(ctx, cudaMemcpyAsync(base_p + o_xyz3 + ch.a0 * 12, xyz3 + ch.a0 * 3, na * 12, cudaMemcpyHostToDevice, st));
+                pack_frames_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(
+                    reinterpret_cast<const float *>(base_p + o_xyz3) + ch.a0 * 3, reinterpret_cast<const float *>(base_p + o_rad),
+                    reinterpret_cast<float4 *>(base_p + o_xyzr) + ch.a0, (uint32_t)na, (uint32_t)fN, (uint32_t)(ch.a0 % (fN ? fN : 1)));
+                ++b->launches_last;
+            } else {
+                CU_TRY(ctx, cudaMemcpyAsync(base_p + o_xyzr + ch.a0 * 16, xyzr + ch.a0 * 4, na * 16, cudaMemcpyHostToDevice, st));
+            }
+            if (id_class)
+                CU_TRY(ctx, cudaMemcpyAsync(base_p + o_cls + ch.a0 * 4, id_class + ch.a0, na * 4, cudaMemcpyHostToDevice, st));
+        }
+        if ((rc = enqueue_chunk(b, variant, ch, kbase, st, &b->launches_last)) != 0) return rc;
+        if (na && out->counts)
+            CU_TRY(ctx, cudaMemcpyAsync(out->counts + ch.a0, base_p + o_cnt + ch.a0 * 4, na * 4, cudaMemcpyDeviceToHost, st));
+        if (na && out->atom_sasa)
+            CU_TRY(ctx, cudaMemcpyAsync(out->atom_sasa + ch.a0, base_p + o_atom + ch.a0 * 4, na * 4, cudaMemcpyDeviceToHost, st));
+        if (out->seg_sasa && ch.g1 > ch.g0)
+            CU_TRY(ctx, cudaMemcpyAsync(out->seg_sasa + ch.g0, base_p + o_seg + ch.g0 * 4, (ch.g1 - ch.g0) * 4, cudaMemcpyDeviceToHost, st));
+        if (out->protein && ch.s1 > ch.s0)
+            CU_TRY(ctx, cudaMemcpyAsync(out->protein + 3 * (size_t)ch.s0, base_p + o_prot + 12 * (size_t)ch.s0,
+                                        12 * (size_t)(ch.s1 - ch.s0), cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kStreams; ++i) CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[i]));
+    CU_TRY(ctx, cudaEventRecord(ev1, ctx->streams[0]));
+    CU_TRY(ctx, cudaEventSynchronize(ev1));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    b->last = sasa_b200_stats{};
+    b->last.kernel_ms = ms;  // device-side span of the whole pipelined run (copies overlapped with kernels)
+    b->last.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    rc = finish_run(b, stats);
+    cudaMemset(ctx->d_err, 0, sizeof(int));
+    cudaMemset(ctx->d_stat, 0, 3 * sizeof(unsigned long long));
+    return rc;
+}
+
+int sasa_b200_batch_run_host(sasa_b200_batch *b, const float *xyzr, const uint32_t *id_class,
+                             const sasa_b200_params *params, const sasa_b200_outputs *out, sasa_b200_stats *stats) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    return run_host_impl(b, xyzr, nullptr, nullptr, id_class, params, out, stats);
+}
+
+int sasa_b200_batch_run_frames_host(sasa_b200_batch *b, const float *xyz, const float *radii,
+                                    const sasa_b200_params *params, const sasa_b200_outputs *out, sasa_b200_stats *stats) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    if (!xyz || !radii) return fail(b->ctx, SASA_B200_ERR_INVALID_ARGUMENT, "xyz / radii is NULL");
+    return run_host_impl(b, nullptr, xyz, radii, nullptr, params, out, stats);
+}
+
+int sasa_b200_run_batch(sasa_b200_ctx *ctx, const float *xyzr, const uint32_t *id_class, const uint64_t *struct_off,
+                        size_t S, const uint32_t *seg_be, const uint64_t *struct_seg_off, const uint8_t *seg_polar,
+                        const sasa_b200_params *params, const sasa_b200_outputs *out, sasa_b200_stats *stats) {
+    sasa_b200_batch *b = nullptr;
+    int rc = sasa_b200_batch_create(ctx, struct_off, S, seg_be, struct_seg_off, seg_polar, &b);
+    if (rc) return rc;
+    rc = sasa_b200_batch_run_host(b, xyzr, id_class, params, out, stats);
+    sasa_b200_batch_destroy(b);
+    return rc;
+}
+
+int sasa_b200_calculate_sasa_internal(sasa_b200_ctx *ctx, const float *xyzr, const uint64_t *ids, size_t n_atoms,
+                                      float probe_radius, size_t n_points, ptrdiff_t threads, float *out_sasa,
+                                      uint32_t *out_counts) {
+    if (!ctx) return SASA_B200_ERR_INVALID_ARGUMENT;
+    if (n_atoms == 0) return SASA_B200_OK;  // empty in, empty out (tests/sanity.rs:148-157)
+    if (!xyzr || !out_sasa) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "xyzr / out_sasa is NULL");
+    if (n_points > (1u << 24)) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "n_points too large");
+    // Atom.id only matters through equality: rank the ids densely, and drop them when all are distinct.
+    std::vector<uint32_t> cls;
+    if (ids) {
+        std::unordered_map<uint64_t, uint32_t> rank;
+        rank.reserve(n_atoms * 2);
+        cls.resize(n_atoms);
+        for (size_t i = 0; i < n_atoms; ++i) cls[i] = rank.emplace(ids[i], (uint32_t)rank.size()).first->second;
+        if (rank.size() == n_atoms) cls.clear();
+    }
+    const uint64_t off[2] = {0, n_atoms};
+    sasa_b200_params prm{probe_radius, (uint32_t)n_points, 8, (int32_t)threads, 0};
+    sasa_b200_outputs out{out_counts, out_sasa, nullptr, nullptr};
+    return sasa_b200_run_batch(ctx, xyzr, cls.empty() ? nullptr : cls.data(), off, 1, nullptr, nullptr, nullptr, &prm, &out, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,400 @@
+// sasa_device.cuh -- device-side building blocks of the B200 Shrake-Rupley engine.
+//
+// Arithmetic contract (what makes per-atom exposed-point counts bit-identical to the
+// reference's CPU path, /root/reference/src/lib.rs:94-224):
+//   v      = c_i - c_j                       three IEEE subtractions           (:129-131)
+//   vmag   = (vx*vx + vy*vy) + vz*vz         unfused, left to right            (:132-133)
+//   limit  = ((t_j - vmag) - r2) / (2*r)     IEEE division                     (:135-136)
+//   body   : dot = fma(sx,vx, fma(sy,vy, sz*vz)),  occluded iff dot <  limit   (:143-147)
+//   tail   : dot = (sx*vx + sy*vy) + sz*vz,        occluded iff dot <= limit   (:185-186)
+// Every operation on that path is written with an explicit round-to-nearest intrinsic so
+// that nvcc can neither contract nor re-associate it, whatever -fmad says.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sasa {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kNbCap = 128;           // neighbour entries staged per warp
+constexpr float kCutSlack = 1.0e-3f;  // Angstrom; keeps exactly-tangent pairs in the list
+constexpr float kCellSafety = 1.0002f;
+constexpr double kBoundaryTol = 1.0e-5;
+
+struct KParams {
+    // batch (device pointers)
+    const float4 *xyzr;
+    const uint32_t *cls;          // nullable
+    const uint32_t *struct_off;   // S+1
+    const uint32_t *order;        // structures handled by this launch
+    uint32_t n_work;
+    uint32_t *work_counter;
+    const uint2 *seg_be;          // nullable
+    const uint32_t *struct_seg_off;
+    const uint8_t *seg_polar;     // nullable
+    // outputs (nullable)
+    uint32_t *out_counts;
+    float *out_atom;
+    float *out_seg;
+    float *out_protein;
+    // sphere points (SoA) and run parameters
+    const float *px, *py, *pz;
+    uint32_t n_points, n_body;
+    float inv_n, probe;
+    float near2;                  // squared centre distance below which a neighbour is "near"
+    // shared-memory capacities of this launch
+    uint32_t nmax, cmax;
+    uint32_t flags;
+    int *err_flag;
+    unsigned long long *stat;     // [0] boundary points, [1] neighbour pairs, [2] streamed atoms
+};
+
+struct Grid {
+    float minx, miny, minz, inv_c;
+    int nx, ny, nz, e;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ int cell_coord(float x, float mn, float inv_c, int n) {
+    int c = (int)(__fmul_rn(__fsub_rn(x, mn), inv_c));
+    return min(max(c, 0), n - 1);
+}
+
+// (vx, vy, vz, limit) of neighbour j as seen from atom i -- the per-pair setup of lib.rs:128-136.
+__device__ __forceinline__ float4 make_entry(const float4 ai, const float4 aj, float probe, float r2, float two_r,
+                                             float *vmag_out) {
+    const float vx = __fsub_rn(ai.x, aj.x), vy = __fsub_rn(ai.y, aj.y), vz = __fsub_rn(ai.z, aj.z);
+    const float vmag = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+    const float tj = __fadd_rn(aj.w, probe);
+    const float t = __fmul_rn(tj, tj);
+    const float limit = __fdiv_rn(__fsub_rn(__fsub_rn(t, vmag), r2), two_r);
+    *vmag_out = vmag;
+    return make_float4(vx, vy, vz, limit);
+}
+
+__device__ __forceinline__ float dot_body(float sx, float sy, float sz, const float4 e) {
+    return __fmaf_rn(sx, e.x, __fmaf_rn(sy, e.y, __fmul_rn(sz, e.z)));
+}
+__device__ __forceinline__ float dot_tail(float sx, float sy, float sz, const float4 e) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(sx, e.x), __fmul_rn(sy, e.y)), __fmul_rn(sz, e.z));
+}
+__device__ __forceinline__ bool occl(float sx, float sy, float sz, bool tail, const float4 e) {
+    return tail ? (dot_tail(sx, sy, sz, e) <= e.w) : (dot_body(sx, sy, sz, e) < e.w);
+}
+
+// Area expression of lib.rs:220-222: ((4*pi_f32 * r2) * count) * (1/n).
+__device__ __forceinline__ float atom_area(float radius, float probe, float count, float inv_n) {
+    const float r = __fadd_rn(radius, probe);
+    const float r2 = __fmul_rn(r, r);
+    const float sa = __fmul_rn(12.566370614359172f, r2);
+    return __fmul_rn(__fmul_rn(sa, count), inv_n);
+}
+
+// ---------------------------------------------------------------------------------------
+// Candidate enumeration around one atom: the (2e+1)^2 cell rows that can hold a neighbour,
+// each a contiguous range of the cell-sorted atom array, flattened into one index space so
+// that all 32 lanes test a candidate per step.
+// ---------------------------------------------------------------------------------------
+struct Rows {
+    int start, incl, excl, total;  // per lane (= per row) range start, inclusive/exclusive prefix; warp total
+};
+
+template <typename CellT>
+__device__ __forceinline__ Rows rows_of(const Grid &g, const CellT *cell, int cx, int cy, int cz) {
+    const int lane = lane_id();
+    const int w = 2 * g.e + 1;
+    const int dy = lane % w - g.e, dz = lane / w - g.e;
+    const int y = cy + dy, z = cz + dz;
+    const bool ok = lane < w * w && y >= 0 && y < g.ny && z >= 0 && z < g.nz;
+    int start = 0, len = 0;
+    if (ok) {
+        const int x0 = max(cx - g.e, 0), x1 = min(cx + g.e, g.nx - 1);
+        const int base = (z * g.ny + y) * g.nx;
+        start = (int)cell[base + x0];
+        len = (int)cell[base + x1 + 1] - start;
+    }
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += t;
+    }
+    Rows r;
+    r.start = start;
+    r.incl = incl;
+    r.excl = incl - len;
+    r.total = __shfl_sync(kFull, incl, 31);
+    return r;
+}
+
+// Flat candidate index -> position in the sorted atom array (valid only when idx < rows.total).
+__device__ __forceinline__ int row_lookup(const Rows &r, int idx) {
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int v = __shfl_sync(kFull, r.incl, lo + step - 1);
+        if (v <= idx) lo += step;
+    }
+    lo = min(lo, 31);
+    const int rs = __shfl_sync(kFull, r.start, lo);
+    const int re = __shfl_sync(kFull, r.excl, lo);
+    return rs + (idx - re);
+}
+
+// ---------------------------------------------------------------------------------------
+// Streaming (list-free) evaluation of one atom: always correct for any density, used when
+// the neighbour list would overflow the per-warp staging area, when boundary statistics
+// are requested and as the in-kernel cross-check of the fast path.
+// Returns the exposed-point count; all lanes receive it.
+// ---------------------------------------------------------------------------------------
+template <typename AtomAcc, typename CellT, bool STATS>
+__device__ float atom_streaming(const KParams &p, const Grid &g, const AtomAcc &atoms, const CellT *cell,
+                                const uint32_t *cls_sorted, int pos, float4 *ent, unsigned long long *boundary) {
+    const int lane = lane_id();
+    const float4 ai = atoms(pos);
+    const float r = __fadd_rn(ai.w, p.probe);
+    const float r2 = __fmul_rn(r, r);
+    const float two_r = __fmul_rn(2.0f, r);
+    const float reach_i = ai.w + 2.0f * p.probe + kCutSlack;
+    const uint32_t cls_i = cls_sorted ? cls_sorted[pos] : 0u;
+    const int cx = cell_coord(ai.x, g.minx, g.inv_c, g.nx), cy = cell_coord(ai.y, g.miny, g.inv_c, g.ny),
+              cz = cell_coord(ai.z, g.minz, g.inv_c, g.nz);
+    const Rows rows = rows_of(g, cell, cx, cy, cz);
+    float exposed = 0.0f;
+    unsigned nbnd = 0;
+    for (uint32_t p0 = 0; p0 < p.n_points; p0 += 128) {
+        float sx[4], sy[4], sz[4];
+        bool occ[4], tail[4], bnd[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t pi = p0 + 32u * s + lane;
+            const bool valid = pi < p.n_points;
+            sx[s] = valid ? __ldg(p.px + pi) : 0.0f;
+            sy[s] = valid ? __ldg(p.py + pi) : 0.0f;
+            sz[s] = valid ? __ldg(p.pz + pi) : 0.0f;
+            occ[s] = !valid;
+            bnd[s] = false;
+            tail[s] = pi >= p.n_body;
+        }
+        for (int t0 = 0; t0 < rows.total; t0 += 32) {
+            const int idx = t0 + lane;
+            const int j = row_lookup(rows, idx);
+            bool acc = false;
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < rows.total && j != pos) {
+                const float4 aj = atoms(j);
+                float vmag;
+                e = make_entry(ai, aj, p.probe, r2, two_r, &vmag);
+                const float cut = reach_i + aj.w;
+                acc = vmag <= cut * cut && !(cls_sorted && cls_sorted[j] == cls_i);
+            }
+            const unsigned m = __ballot_sync(kFull, acc);
+            if (acc) ent[__popc(m & lanemask_lt())] = e;
+            __syncwarp();
+            const int cnt = __popc(m);
+            for (int q = 0; q < cnt; ++q) {
+                const float4 eq = ent[q];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const float d = tail[s] ? dot_tail(sx[s], sy[s], sz[s], eq) : dot_body(sx[s], sy[s], sz[s], eq);
+                    occ[s] = occ[s] || (tail[s] ? (d <= eq.w) : (d < eq.w));
+                    if (STATS) bnd[s] = bnd[s] || (fabs(2.0 * (double)r * ((double)d - (double)eq.w)) <= kBoundaryTol);
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            exposed += (float)__popc(__ballot_sync(kFull, !occ[s]));
+            if (STATS) nbnd += __popc(__ballot_sync(kFull, bnd[s] && (p0 + 32u * s + lane < p.n_points)));
+        }
+    }
+    if (STATS && lane == 0 && nbnd) atomicAdd(boundary, (unsigned long long)nbnd);
+    return exposed;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fast path pieces.
+// ---------------------------------------------------------------------------------------
+
+// Pass 1: positions (in the sorted array) of all atoms within r_i + r_j + 2*probe (+slack) of
+// atom `pos`.  Returns the count, or -1 if it exceeds kNbCap (caller falls back to streaming).
+template <typename AtomAcc, typename CellT, typename IdxT>
+__device__ __forceinline__ int gather_candidates(const KParams &p, const Grid &g, const AtomAcc &atoms,
+                                                 const CellT *cell, const uint32_t *cls_sorted, int pos,
+                                                 const float4 ai, IdxT *cand) {
+    const int lane = lane_id();
+    const float reach_i = ai.w + 2.0f * p.probe + kCutSlack;
+    const uint32_t cls_i = cls_sorted ? cls_sorted[pos] : 0u;
+    const int cx = cell_coord(ai.x, g.minx, g.inv_c, g.nx), cy = cell_coord(ai.y, g.miny, g.inv_c, g.ny),
+              cz = cell_coord(ai.z, g.minz, g.inv_c, g.nz);
+    const Rows rows = rows_of(g, cell, cx, cy, cz);
+    int k = 0;
+    for (int t0 = 0; t0 < rows.total; t0 += 32) {
+        const int idx = t0 + lane;
+        const int j = row_lookup(rows, idx);
+        bool acc = false;
+        if (idx < rows.total && j != pos) {
+            const float4 aj = atoms(j);
+            const float dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            const float cut = reach_i + aj.w;
+            // membership is result-neutral (a superset of the overlapping pairs is all that is needed), so this
+            // test may use contracted arithmetic; the slack absorbs its rounding.
+            acc = d2 <= cut * cut && !(cls_sorted && cls_sorted[j] == cls_i);
+        }
+        const unsigned m = __ballot_sync(kFull, acc);
+        if (m) {
+            const int at = k + __popc(m & lanemask_lt());
+            if (acc && at < kNbCap) cand[at] = (IdxT)j;
+            k += __popc(m);
+        }
+    }
+    __syncwarp();
+    return k <= kNbCap ? k : -1;
+}
+
+// Pass 2: turn candidate positions into (v, limit) entries; "near" neighbours (centre distance^2 < near2) are
+// packed at the front, the rest at the back.  Returns the number of near entries.
+template <typename AtomAcc, typename IdxT>
+__device__ __forceinline__ int build_entries(const KParams &p, const AtomAcc &atoms, const float4 ai, float r2,
+                                             float two_r, const IdxT *cand, int k, float4 *ent) {
+    const int lane = lane_id();
+    int nfront = 0, nback = 0;
+    for (int q0 = 0; q0 < k; q0 += 32) {
+        const int q = q0 + lane;
+        const bool valid = q < k;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        float vmag = 0.0f;
+        if (valid) e = make_entry(ai, atoms((int)cand[q]), p.probe, r2, two_r, &vmag);
+        const bool near = valid && vmag < p.near2;
+        const unsigned mn = __ballot_sync(kFull, near);
+        const unsigned mf = __ballot_sync(kFull, valid && !near);
+        if (valid) {
+            const int at = near ? nfront + __popc(mn & lanemask_lt()) : (k - 1) - (nback + __popc(mf & lanemask_lt()));
+            ent[at] = e;
+        }
+        nfront += __popc(mn);
+        nback += __popc(mf);
+    }
+    __syncwarp();
+    return nfront;
+}
+
+// Phase 1: all points of one 128-point chunk against entries [0, m): one broadcast LDS.128 per neighbour,
+// NBODY pure-body slots (+ NMIX slots that may hold tail points) per lane.
+template <int NBODY, int NMIX>
+__device__ __forceinline__ void phase1(const float4 *ent, int m, const float (&sx)[4], const float (&sy)[4],
+                                       const float (&sz)[4], const bool (&tail)[4], bool (&occ)[4]) {
+#pragma unroll 2
+    for (int q = 0; q < m; ++q) {
+        const float4 e = ent[q];
+#pragma unroll
+        for (int s = 0; s < NBODY; ++s) occ[s] = occ[s] || (dot_body(sx[s], sy[s], sz[s], e) < e.w);
+#pragma unroll
+        for (int s = NBODY; s < NBODY + NMIX; ++s) occ[s] = occ[s] || occl(sx[s], sy[s], sz[s], tail[s], e);
+    }
+}
+
+// Phase 2 (few survivors): lanes run over the remaining entries [m, k), one surviving point at a time.
+__device__ __forceinline__ bool survivor_vs_entries(const float4 *ent, int m, int k, float sx, float sy, float sz,
+                                                    bool tail) {
+    bool hit = false;
+    for (int q = m + lane_id(); q < k; q += 32) {
+        const float4 e = ent[q];
+        hit = hit || occl(sx, sy, sz, tail, e);
+    }
+    return __any_sync(kFull, hit);
+}
+
+// Fast evaluation of one atom whose complete neighbour list sits in ent[0, k) with nfront near entries first.
+// `queue` is per-warp scratch for survivor point indices (kNbCap u16, may alias cand).
+__device__ float atom_fast(const KParams &p, const float4 *ent, int k, int nfront, uint16_t *queue) {
+    const int lane = lane_id();
+    float exposed = 0.0f;
+    int m = min(k, min(max(nfront, 4), 16));
+    for (uint32_t p0 = 0; p0 < p.n_points; p0 += 128) {
+        float sx[4], sy[4], sz[4];
+        bool occ[4], tail[4];
+        const uint32_t rem = p.n_points - p0;
+        const int nslots = rem >= 128 ? 4 : (int)((rem + 31) >> 5);
+        // slots wholly inside the SIMD body; every other used slot is evaluated per lane
+        int nbody = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t pi = p0 + 32u * s + lane;
+            const bool valid = pi < p.n_points;
+            sx[s] = valid ? __ldg(p.px + pi) : 0.0f;
+            sy[s] = valid ? __ldg(p.py + pi) : 0.0f;
+            sz[s] = valid ? __ldg(p.pz + pi) : 0.0f;
+            occ[s] = !valid;
+            tail[s] = pi >= p.n_body;
+            if (p0 + 32u * s + 32u <= p.n_body) nbody = s + 1;
+        }
+        const int nmix = nslots - nbody;
+        if (nbody == 4) phase1<4, 0>(ent, m, sx, sy, sz, tail, occ);
+        else if (nbody == 3 && nmix == 1) phase1<3, 1>(ent, m, sx, sy, sz, tail, occ);
+        else if (nbody == 3) phase1<3, 0>(ent, m, sx, sy, sz, tail, occ);
+        else if (nbody == 2 && nmix == 0) phase1<2, 0>(ent, m, sx, sy, sz, tail, occ);
+        else if (nbody == 1 && nmix == 0) phase1<1, 0>(ent, m, sx, sy, sz, tail, occ);
+        else phase1<0, 4>(ent, m, sx, sy, sz, tail, occ);
+        if (m == k) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) exposed += (float)__popc(__ballot_sync(kFull, !occ[s]));
+            continue;
+        }
+        // survivors -> queue (slot-major order)
+        int ns = 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const unsigned ms = __ballot_sync(kFull, !occ[s]);
+            if (!occ[s]) queue[ns + __popc(ms & lanemask_lt())] = (uint16_t)(32 * s + lane);
+            ns += __popc(ms);
+        }
+        __syncwarp();
+        if (ns == 0) continue;
+        if (ns >= 12) {
+            // many survivors: one survivor per lane, broadcast the remaining entries
+            for (int b = 0; b < ns; b += 32) {
+                const bool have = b + lane < ns;
+                const uint32_t pi = p0 + (have ? (uint32_t)queue[b + lane] : 0u);
+                const float qx = __ldg(p.px + pi), qy = __ldg(p.py + pi), qz = __ldg(p.pz + pi);
+                const bool qt = pi >= p.n_body;
+                bool dead = !have;
+                const bool any_tail = __any_sync(kFull, have && qt);
+                if (!any_tail) {
+                    for (int q = m; q < k; ++q) {
+                        const float4 e = ent[q];
+                        dead = dead || (dot_body(qx, qy, qz, e) < e.w);
+                        if ((q & 3) == 3 && __all_sync(kFull, dead)) break;
+                    }
+                } else {
+                    for (int q = m; q < k; ++q) {
+                        const float4 e = ent[q];
+                        dead = dead || occl(qx, qy, qz, qt, e);
+                        if ((q & 3) == 3 && __all_sync(kFull, dead)) break;
+                    }
+                }
+                exposed += (float)__popc(__ballot_sync(kFull, !dead));
+            }
+        } else {
+            // few survivors: lanes over entries, one survivor at a time
+            for (int t = 0; t < ns; ++t) {
+                const uint32_t pi = p0 + (uint32_t)queue[t];
+                const float qx = __ldg(p.px + pi), qy = __ldg(p.py + pi), qz = __ldg(p.pz + pi);
+                if (!survivor_vs_entries(ent, m, k, qx, qy, qz, pi >= p.n_body)) exposed += 1.0f;
+            }
+        }
+        __syncwarp();
+    }
+    return exposed;
+}
+
+}  // namespace sasa

@@ -1,0 +1,381 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): per-atom exposed-point counts EXACT; per-atom SASA, residue / chain /
+protein sums within 1e-4 relative or 1e-3 A^2 absolute -- in fact asserted bit-identical here, because
+the kernels use the reference's arithmetic and summation order.  Run on the B200 box: pytest -m gpu.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PROBE = 1.4
+REL, ABS = 1e-4, 1e-3     # the north-star floating-point tolerance
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rustsasa_b200 import Engine
+    e = Engine()
+    yield e
+    e.close()
+
+
+def close_enough(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.all(np.abs(a - b) <= np.maximum(ABS, REL * np.abs(b)))
+
+
+def test_sphere_points_match_oracle(eng, oracle):
+    for n in (1, 7, 100, 960, 5000):
+        assert np.array_equal(eng.sphere_points(n), oracle.sphere_points(n))
+
+
+def test_golden_vector_exact(eng, golden):
+    """The reference's own KAT (tests/units.rs:17-43, tests/common/data.rs): exact integer counts."""
+    g = golden.vdw
+    sasa, counts = eng.calculate_sasa_internal(g["xyzr"], None, PROBE, 100, -1, want_counts=True)
+    assert np.array_equal(counts, g["gold_counts"])
+    assert int(counts.sum()) == 16843
+    assert np.abs(sasa - g["gold_sasa"]).max() < 1e-5          # reference asserts epsilon = 25.0
+    assert close_enough(sasa, g["gold_sasa"])
+
+
+@pytest.mark.parametrize("name", ["example.cif", "151L_H3.pdb", "bad_seqadv_1A06.pdb", "2drt", "4xfj"])
+@pytest.mark.parametrize("n_points", [100, 960])
+def test_structure_all_levels_bit_exact(eng, oracle, golden, name, n_points):
+    s = golden.structure(name)
+    o = oracle.calculate_sasa_internal(s["xyzr"], PROBE, n_points)
+    n = s["xyzr"].shape[0]
+    # residue level
+    b = eng.batch([0, n], s["seg_be"], [0, len(s["seg_be"])], s["polar"])
+    r = b.run_host(s["xyzr"], n_points=n_points)
+    assert np.array_equal(r.counts, o["counts"])
+    assert np.array_equal(r.atom_sasa, o["sasa"])
+    assert np.array_equal(r.seg_sasa, oracle.segment_sums(o["sasa"], s["seg_be"]))
+    assert np.array_equal(r.protein[0], oracle.protein_totals(o["sasa"], s["seg_be"], s["polar"]))
+    assert r.stats["streamed_atoms"] == 0
+    b.close()
+    # chain level
+    ch = golden.chain_ranges(s)
+    b = eng.batch([0, n], ch, [0, len(ch)])
+    r = b.run_host(s["xyzr"], n_points=n_points, want=("seg",))
+    want = oracle.segment_sums(o["sasa"], ch)
+    assert close_enough(r.seg_sasa, want)
+    if n <= 16384:
+        assert np.array_equal(r.seg_sasa, want)
+    b.close()
+
+
+def test_reference_totals(eng, golden):
+    """tests/units.rs:117 (20131.227 @ 960 points) and Appendix A values."""
+    s = golden.structure("example.cif")
+    n = s["xyzr"].shape[0]
+    b = eng.batch([0, n], s["seg_be"], [0, len(s["seg_be"])], s["polar"])
+    r = b.run_host(s["xyzr"], n_points=960, want=("counts", "protein"))
+    assert int(r.counts.sum()) == 157016
+    assert r.protein[0, 0] == np.float32(20131.227)
+    r = b.run_host(s["xyzr"], n_points=100, want=("counts", "protein"))
+    assert int(r.counts.sum()) == 16326 and abs(float(r.protein[0, 0]) - 20097.68) < 0.01
+    b.close()
+
+
+@pytest.mark.parametrize("n_points,lanes", [(1, 8), (3, 4), (37, 8), (50, 8), (100, 4), (100, 16), (128, 8), (129, 16),
+                                            (200, 8), (200, 16), (333, 16), (1000, 16)])
+def test_point_counts_and_lane_rules(eng, oracle, golden, n_points, lanes):
+    """Body / tail split for every mirrored reference build (src/lib.rs:104-106, :162-218)."""
+    s = golden.structure("151L_H3.pdb")
+    n = s["xyzr"].shape[0]
+    b = eng.batch([0, n])
+    r = b.run_host(s["xyzr"], n_points=n_points, simd_lanes=lanes, want=("counts", "atom"))
+    o = oracle.calculate_sasa_internal(s["xyzr"], PROBE, n_points, lanes=lanes)
+    assert np.array_equal(r.counts, o["counts"])
+    assert np.array_equal(r.atom_sasa, o["sasa"])
+    b.close()
+
+
+@pytest.mark.parametrize("probe", [0.0, 0.5, 1.4, 2.0, 3.5])
+def test_probe_radii(eng, oracle, golden, probe):
+    s = golden.structure("bad_seqadv_1A06.pdb")
+    sasa, counts = eng.calculate_sasa_internal(s["xyzr"], None, probe, 100, -1, want_counts=True)
+    o = oracle.calculate_sasa_internal(s["xyzr"], probe, 100)
+    assert np.array_equal(counts, o["counts"]) and np.array_equal(sasa, o["sasa"])
+
+
+def _concat(structs):
+    xyzr = np.concatenate([s["xyzr"] for s in structs])
+    off = np.cumsum([0] + [s["xyzr"].shape[0] for s in structs]).astype(np.uint64)
+    seg = np.concatenate([s["seg_be"] for s in structs])
+    soff = np.cumsum([0] + [len(s["seg_be"]) for s in structs]).astype(np.uint64)
+    pol = np.concatenate([s["polar"] for s in structs])
+    return xyzr, off, seg, soff, pol
+
+
+def test_whole_quality_set_in_one_batch(eng, golden):
+    """All 90 fixture structures (317 .. 32k atoms: every shared-memory bucket and the large path) in ONE
+    batch call vs the oracle per structure; also restates tests/quality.rs RMSE on the GPU results."""
+    from oracle import load
+    fast = load(fast=True)
+    structs = [golden.structure(n) for n in golden.names]
+    xyzr, off, seg, soff, pol = _concat(structs)
+    b = eng.batch(off, seg, soff, pol)
+    r = b.run_host(xyzr)
+    fs, ours = [], []
+    for k, s in enumerate(structs):
+        a0, a1, g0, g1 = int(off[k]), int(off[k + 1]), int(soff[k]), int(soff[k + 1])
+        o = fast.calculate_sasa_internal(s["xyzr"], PROBE, 100)
+        assert np.array_equal(r.counts[a0:a1], o["counts"]), s["name"]
+        assert np.array_equal(r.atom_sasa[a0:a1], o["sasa"]), s["name"]
+        assert np.array_equal(r.seg_sasa[g0:g1], fast.segment_sums(o["sasa"], s["seg_be"])), s["name"]
+        assert close_enough(r.protein[k], fast.protein_totals(o["sasa"], s["seg_be"], s["polar"])), s["name"]
+        if s["name"] in golden.freesasa:
+            segv = r.seg_sasa[g0:g1].astype(np.float64)
+            for ci, label in enumerate(s["chains"]):
+                if label in golden.freesasa[s["name"]]:
+                    fs.append(golden.freesasa[s["name"]][label])
+                    ours.append(segv[s["res_chain"] == ci].sum())
+    rmse = float(np.sqrt(np.mean((np.array(fs) - np.array(ours)) ** 2)))
+    assert rmse <= 43.99 + 20.0 and abs(rmse - 43.99) < 0.5
+    b.close()
+
+
+def test_streaming_kernel_and_boundary_stats(eng, oracle, golden):
+    from rustsasa_b200 import _lib
+    s = golden.structure("example.cif")
+    n = s["xyzr"].shape[0]
+    b = eng.batch([0, n])
+    fastp = b.run_host(s["xyzr"], want=("counts",))
+    stream = b.run_host(s["xyzr"], want=("counts",), flags=_lib.FLAG_FORCE_STREAMING)
+    assert np.array_equal(fastp.counts, stream.counts)
+    assert stream.stats["streamed_atoms"] == n and fastp.stats["streamed_atoms"] == 0
+    st = b.run_host(s["xyzr"], want=("counts",), flags=_lib.FLAG_BOUNDARY_STATS)
+    o = oracle.calculate_sasa_internal(s["xyzr"], PROBE, 100, boundary_tol=1e-5)
+    assert np.array_equal(st.counts, o["counts"])
+    assert st.stats["boundary_points"] == int(o["boundary"].sum())
+    b.close()
+
+
+def test_duplicate_ids(eng, oracle):
+    xyzr = np.array([[0, 0, 0, 2.0], [1.0, 0, 0, 2.0], [0.5, 1.0, 0.0, 1.5]], np.float32)
+    ids = np.array([7, 7, 9], np.uint64)
+    sasa, counts = eng.calculate_sasa_internal(xyzr, ids, PROBE, 100, -1, want_counts=True)
+    o = oracle.calculate_sasa_internal(xyzr, PROBE, 100, ids=ids)
+    assert np.array_equal(counts, o["counts"]) and np.array_equal(sasa, o["sasa"])
+    sasa2, counts2 = eng.calculate_sasa_internal(xyzr, np.array([1, 2, 3], np.uint64), PROBE, 100, -1, want_counts=True)
+    assert np.array_equal(counts2, oracle.calculate_sasa_internal(xyzr, PROBE, 100)["counts"])
+    assert counts2[0] < counts[0]
+
+
+def test_multi_model_id_classes_in_batch(eng, oracle, golden):
+    """Two overlaid copies of a structure sharing ids (a multi-model file): copies never occlude each other."""
+    s = golden.structure("2drt")
+    n = s["xyzr"].shape[0]
+    xyzr = np.concatenate([s["xyzr"], s["xyzr"] + np.array([0.3, 0, 0, 0], np.float32)])
+    cls = np.concatenate([np.arange(n), np.arange(n)]).astype(np.uint32)
+    b = eng.batch([0, 2 * n])
+    r = b.run_host(xyzr, cls, want=("counts",))
+    o = oracle.calculate_sasa_internal(xyzr, PROBE, 100, ids=cls.astype(np.uint64))
+    assert np.array_equal(r.counts, o["counts"])
+    b.close()
+
+
+def _area(r):
+    return 4.0 * np.pi * r * r
+
+
+def test_sanity_closed_forms(eng):
+    """tests/sanity.rs:20-157 through the raw-atoms entry point, 50,000 points, 0.5 %."""
+    from rustsasa_b200 import Atom, calculate_sasa_internal
+    n, tol = 50000, 0.005
+    A = lambda x, y, z, r, i: Atom([x, y, z], r, i)   # noqa: E731
+    one = calculate_sasa_internal([A(0, 0, 0, 2.0, 1)], PROBE, n, 1, engine=eng)
+    assert abs(one[0] / _area(3.4) - 1) < tol
+    two = calculate_sasa_internal([A(0, 0, 0, 2.0, 1), A(10, 0, 0, 2.0, 2)], PROBE, n, 1, engine=eng)
+    assert abs(two[0] / _area(3.4) - 1) < tol and abs(two[1] / _area(3.4) - 1) < tol
+    assert abs(float(two.sum()) / (2 * _area(3.4)) - 1) < tol
+    r, d = 3.4, 4.0
+    exp = _area(r) - 2 * np.pi * r * (r - d / 2)
+    ov = calculate_sasa_internal([A(0, 0, 0, 2.0, 1), A(d, 0, 0, 2.0, 2)], PROBE, n, 1, engine=eng)
+    assert abs(ov[0] / exp - 1) < tol and abs(ov[1] / exp - 1) < tol
+    cont = calculate_sasa_internal([A(0, 0, 0, 10.0, 1), A(2, 0, 0, 2.0, 2)], PROBE, n, 1, engine=eng)
+    assert abs(cont[0] / _area(11.4) - 1) < tol and cont[1] <= tol
+    d = 5.0
+    cap = 2 * np.pi * r * (r - d / 2)
+    ch = calculate_sasa_internal([A(0, 0, 0, 2.0, 1), A(d, 0, 0, 2.0, 2), A(2 * d, 0, 0, 2.0, 3)], PROBE, n, 1, engine=eng)
+    assert abs(ch[0] / (_area(r) - cap) - 1) < tol and abs(ch[2] / (_area(r) - cap) - 1) < tol
+    assert abs(ch[1] / (_area(r) - 2 * cap) - 1) < tol
+    assert calculate_sasa_internal([], PROBE, n, 1, engine=eng).shape == (0,)
+
+
+def test_edge_cases(eng, oracle):
+    from rustsasa_b200 import SasaB200Error
+    # empty batch, empty structures between real ones, single atom, coincident atoms
+    b = eng.batch([0])
+    r = b.run_host(np.zeros((0, 4), np.float32))
+    assert r.counts.shape == (0,) and r.protein.shape == (0, 3)
+    b.close()
+    xyzr = np.array([[1, 2, 3, 1.5], [5, 5, 5, 1.8], [5, 5, 5, 1.8], [5.5, 5, 5, 1.2]], np.float32)
+    b = eng.batch([0, 0, 1, 1, 4, 4], np.array([[0, 1], [0, 0], [0, 3], [1, 3]], np.uint32), [0, 0, 1, 1, 4, 4],
+                  np.array([1, 0, 1, 0], np.uint8))
+    r = b.run_host(xyzr)
+    o1 = oracle.calculate_sasa_internal(xyzr[:1], PROBE, 100)
+    o2 = oracle.calculate_sasa_internal(xyzr[1:], PROBE, 100)
+    assert list(r.counts[:1]) == [100] and np.array_equal(r.counts[1:], o2["counts"])
+    assert np.array_equal(r.atom_sasa, np.concatenate([o1["sasa"], o2["sasa"]]))
+    assert r.seg_sasa[1] == 0.0                                   # empty residue reports 0.0 (tests/io.rs:164-224)
+    assert r.seg_sasa[3] == oracle.segment_sums(o2["sasa"], [[1, 3]])[0]
+    assert np.all(r.protein[0] == 0) and np.all(r.protein[1, 0] == o1["sasa"][0])
+    b.close()
+    # non-finite input: the reference panics; the C ABI reports status 4 and does not crash
+    bad = xyzr.copy()
+    bad[2, 1] = np.nan
+    with pytest.raises(SasaB200Error) as ei:
+        eng.calculate_sasa_internal(bad)
+    assert ei.value.code == 4
+    assert eng.calculate_sasa_internal(xyzr).shape == (4,)        # the context stays usable
+    # invalid arguments
+    with pytest.raises(SasaB200Error):
+        eng.batch([0, 4]).run_host(xyzr, n_points=0)
+    with pytest.raises(SasaB200Error):
+        eng.batch([0, 4]).run_host(xyzr, simd_lanes=5)
+    with pytest.raises(SasaB200Error):
+        eng.batch([0, 4], np.array([[0, 9]], np.uint32), [0, 1])
+
+
+def test_dense_cluster_overflows_to_streaming(eng, oracle):
+    """More than 128 neighbours per atom (never a protein, but legal input): the staging area overflows and
+    the streaming kernel takes over with identical results."""
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(scale=2.0, size=(600, 3)).astype(np.float32)
+    xyzr = np.concatenate([xyz, np.full((600, 1), 1.7, np.float32)], axis=1)
+    b = eng.batch([0, 600])
+    r = b.run_host(xyzr, want=("counts",))
+    assert np.array_equal(r.counts, oracle.calculate_sasa_internal(xyzr, PROBE, 100)["counts"])
+    assert r.stats["streamed_atoms"] > 0
+    b.close()
+
+
+def test_sparse_and_elongated_structures(eng, oracle):
+    """Cell grid growth: a 2,000 A long string of atoms and widely scattered atoms."""
+    rng = np.random.default_rng(11)
+    n = 1500
+    line = np.stack([np.linspace(0, 2000, n), rng.normal(size=n), rng.normal(size=n)], axis=1)
+    scat = rng.uniform(-400, 400, size=(n, 3))
+    for P in (line, scat):
+        xyzr = np.concatenate([P, rng.choice([1.4, 1.6, 1.9], size=(n, 1))], axis=1).astype(np.float32)
+        sasa, counts = eng.calculate_sasa_internal(xyzr, None, PROBE, 100, -1, want_counts=True)
+        assert np.array_equal(counts, oracle.calculate_sasa_internal(xyzr, PROBE, 100)["counts"])
+
+
+def test_frames_entry_point(eng, oracle):
+    from rustsasa_b200 import workloads as W
+    md = W.md_trajectory(n_frames=6, n_atoms=1200)
+    F, N = md.xyz.shape[:2]
+    off = (np.arange(F + 1) * N).astype(np.uint64)
+    seg = np.tile(md.seg_be, (F, 1))
+    soff = (np.arange(F + 1) * len(md.seg_be)).astype(np.uint64)
+    b = eng.batch(off, seg, soff, np.tile(md.seg_polar, F))
+    r = b.run_frames_host(md.xyz, md.radii, want=("counts", "seg", "protein"))
+    for f in range(F):
+        xyzr = np.concatenate([md.xyz[f], md.radii[:, None]], axis=1)
+        o = oracle.calculate_sasa_internal(xyzr, PROBE, 100)
+        assert np.array_equal(r.counts[f * N:(f + 1) * N], o["counts"])
+        assert np.array_equal(r.protein[f], oracle.protein_totals(o["sasa"], md.seg_be, md.seg_polar))
+    b.close()
+
+
+def test_large_structure_path(eng, golden):
+    """cfg4-style single large structure (global cell list) vs the oracle, atom level."""
+    from oracle import load
+    from rustsasa_b200 import workloads as W
+    fast = load(fast=True)
+    a = W.large_assembly(40000)
+    sasa, counts = eng.calculate_sasa_internal(a.xyzr, None, PROBE, 100, -1, want_counts=True)
+    o = fast.calculate_sasa_internal(a.xyzr, PROBE, 100, threads=-1)
+    assert np.array_equal(counts, o["counts"]) and np.array_equal(sasa, o["sasa"])
+    c = W.capsid_shell(60000)
+    b = eng.batch(c.struct_off, c.seg_be, c.struct_seg_off, c.seg_polar)
+    r = b.run_host(c.xyzr, n_points=960)
+    o = fast.calculate_sasa_internal(c.xyzr, PROBE, 960, threads=-1)
+    assert np.array_equal(r.counts, o["counts"])
+    assert np.array_equal(r.seg_sasa, fast.segment_sums(o["sasa"], c.seg_be))
+    assert close_enough(r.protein[0], fast.protein_totals(o["sasa"], c.seg_be, c.seg_polar))
+    b.close()
+
+
+def test_proteome_batch_sample_and_invariants(eng):
+    """cfg2 shape at reduced count: oracle parity on every structure, then size-independent properties at
+    larger scale -- permutation equivariance of per-atom counts, and batch == one-by-one."""
+    from oracle import load
+    from rustsasa_b200 import workloads as W
+    fast = load(fast=True)
+    data = W.proteome_batch(300)
+    b = eng.batch(data.struct_off, data.seg_be, data.struct_seg_off, data.seg_polar)
+    r = b.run_host(data.xyzr, want=("counts", "seg"))
+    o = fast.run_batch(data.xyzr, data.struct_off, seg_be=data.seg_be, struct_seg_off=data.struct_seg_off)
+    assert np.array_equal(r.counts, o["counts"])
+    assert np.array_equal(r.seg_sasa, o["seg"])
+    assert r.stats["streamed_atoms"] == 0
+    # device-resident entry point gives the same answer
+    import torch
+    d_xyzr = torch.from_numpy(data.xyzr).cuda()
+    d_counts = torch.zeros(data.n_atoms, dtype=torch.int32, device="cuda")
+    d_seg = torch.zeros(len(data.seg_be), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    b.run_device(d_xyzr, counts=d_counts, seg_sasa=d_seg)
+    b.sync()
+    assert np.array_equal(d_counts.cpu().numpy().view(np.uint32), o["counts"])
+    assert np.array_equal(d_seg.cpu().numpy(), o["seg"])
+    b.close()
+    # permutation equivariance (exact: the per-pair arithmetic does not depend on atom order)
+    rng = np.random.default_rng(0)
+    s0, s1 = int(data.struct_off[3]), int(data.struct_off[4])
+    x = data.xyzr[s0:s1]
+    perm = rng.permutation(x.shape[0])
+    c1 = eng.calculate_sasa_internal(x, want_counts=True)[1]
+    c2 = eng.calculate_sasa_internal(x[perm], want_counts=True)[1]
+    assert np.array_equal(c1[perm], c2) and np.array_equal(c1, o["counts"][s0:s1])
+
+
+def test_options_api_process_many(eng, tmp_path):
+    """SASAOptions mirror: levels, filters and error behaviour on a hand-written PDB."""
+    from rustsasa_b200 import (ProteinLevel, ResidueLevel, ChainLevel, AtomLevel, SASACalcError, SASAOptions,
+                               read_structure)
+    pdb = tmp_path / "mini.pdb"
+    lines = [
+        "ATOM      1  N   ALA A   1      11.104   6.134  -6.504  1.00  0.00           N",
+        "ATOM      2  CA  ALA A   1      11.639   6.071  -5.147  1.00  0.00           C",
+        "ATOM      3  C   ALA A   1      13.090   5.613  -5.183  1.00  0.00           C",
+        "ATOM      4  O   ALA A   1      13.704   5.557  -6.250  1.00  0.00           O",
+        "ATOM      5  CB  ALA A   1      10.813   5.126  -4.289  1.00  0.00           C",
+        "ATOM      6  H   ALA A   1      10.500   6.900  -6.700  1.00  0.00           H",
+        "ATOM      7  N   SER B   2      13.645   5.285  -4.023  1.00  0.00           N",
+        "ATOM      8  CA  SER B   2      15.032   4.833  -3.923  1.00  0.00           C",
+        "ATOM      9  C   SER B   2      15.261   4.076  -2.622  1.00  0.00           C",
+        "ATOM     10  O   SER B   2      14.338   3.873  -1.833  1.00  0.00           O",
+        "ATOM     11  CB  SER B   2      15.994   6.014  -4.011  1.00  0.00           C",
+        "ATOM     12  OG  SER B   2      15.800   6.900  -2.920  1.00  0.00           O",
+        "HETATM   13  O   HOH B 101      20.000   6.900  -2.920  1.00  0.00           O",
+        "END",
+    ]
+    pdb.write_text("\n".join(lines) + "\n")
+    st = read_structure(str(pdb))
+    atoms = SASAOptions(AtomLevel).process(st, eng)
+    assert atoms.shape == (11,)                       # hydrogen and HETATM dropped
+    res = SASAOptions(ResidueLevel).process(st, eng)
+    assert [(r.name, r.chain_id, r.is_polar) for r in res] == [("ALA", "A", False), ("SER", "B", True), ("HOH", "B", False)]
+    assert res[2].value == 0.0                        # excluded HETATM residue reports 0.0
+    chains = SASAOptions(ChainLevel).process(st, eng)
+    assert [c.name for c in chains] == ["A", "B"]
+    prot = SASAOptions(ProteinLevel).process(st, eng)
+    assert abs(prot.global_total - float(atoms.sum(dtype=np.float32))) < 1e-3
+    assert abs(prot.polar_total - res[1].value) < 1e-4 and abs(chains[0].value - res[0].value) < 1e-4
+    assert abs(prot.polar_total + prot.non_polar_total - prot.global_total) < 1e-2
+    het = SASAOptions(AtomLevel).with_include_hetatms(True).process(st, eng)
+    assert het.shape == (12,)
+    # RadiusMissing is returned per structure by process_many (directory mode logs and continues) ...
+    out = SASAOptions(AtomLevel).with_include_hydrogens(True).process_many([st, st], eng)
+    assert all(isinstance(o, SASACalcError) and o.kind == "RadiusMissing" for o in out)
+    ok = SASAOptions(AtomLevel).with_include_hydrogens(True).with_allow_vdw_fallback(True).process(st, eng)
+    assert ok.shape == (12,)
