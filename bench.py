@@ -216,7 +216,12 @@ def main():
     # ---- device-resident leg (value) ---------------------------------------------------------------
     d_xyzr = torch.from_numpy(data.xyzr).cuda()
     d_seg = torch.zeros(G, dtype=torch.float32, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    # the kernels are launched on this (non-default) torch stream, and so are the timing events
+    tstream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def barrier():
         if world > 1:
