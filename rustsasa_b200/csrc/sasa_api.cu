@@ -40,7 +40,8 @@ struct Points {
 struct SmallCfg {
     int nt, minb;
     uint32_t nmax, cmax;
-    size_t smem[2];  // without / with id classes
+    size_t smem[2];  // dynamic shared memory limit set on the kernel: without / with id classes
+    int proto;
 };
 
 constexpr int kStreams = 3;
@@ -116,64 +117,55 @@ int get_points(sasa_b200_ctx *ctx, uint32_t n, const float **px) {
     return SASA_B200_OK;
 }
 
-template <int NT, int MINB>
-cudaError_t launch_small(const KParams &kp, bool has_cls, int grid, size_t smem, cudaStream_t st) {
-    if (has_cls) {
-        sasa_small_kernel<NT, MINB, true><<<grid, NT, smem, st>>>(kp);
-    } else {
-        sasa_small_kernel<NT, MINB, false><<<grid, NT, smem, st>>>(kp);
-    }
-    return cudaGetLastError();
+// Shared-memory configurations of the fused kernel, smallest atom capacity first.  nmax is derived from the
+// per-CTA budget that lets `minb` CTAs share one SM (228 KB per SM, 1 KB reserved per CTA, 227 KB per CTA max).
+typedef void (*SmallKernel)(const KParams);
+struct Proto {
+    int nt, minb;
+    uint32_t cmax;
+    SmallKernel fn[2];   // without / with id classes
+};
+#define SASA_PROTO(NT, MINB, CMAX) \
+    Proto { NT, MINB, CMAX, { sasa_small_kernel<NT, MINB, false>, sasa_small_kernel<NT, MINB, true> } }
+const Proto kProtos[] = {SASA_PROTO(256, 3, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(256, 2, 8192),
+                         SASA_PROTO(512, 1, 16384)};
+constexpr int kNumProtos = sizeof(kProtos) / sizeof(kProtos[0]);
+
+size_t cfg_budget(const sasa_b200_ctx *ctx, int minb) {
+    return std::min<size_t>(ctx->smem_optin, (228 * 1024) / minb - 1024);
 }
 
-template <int NT, int MINB>
-cudaError_t set_smem_attr(size_t s0, size_t s1) {
-    cudaError_t e = cudaFuncSetAttribute(sasa_small_kernel<NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s0);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(sasa_small_kernel<NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
-}
-
-// Shared-memory configurations of the fused kernel, smallest first.  nmax is derived from the per-CTA
-// budget that lets `minb` CTAs share one SM (228 KB per SM, 1 KB reserved per CTA, 227 KB per CTA max).
 int build_cfgs(sasa_b200_ctx *ctx) {
-    struct Proto { int nt, minb; uint32_t cmax; };
-    const Proto protos[] = {{256, 3, 4096}, {256, 2, 8192}, {512, 1, 16384}};
-    for (const Proto &pr : protos) {
-        const size_t budget = std::min<size_t>(ctx->smem_optin, (228 * 1024) / pr.minb - 1024);
-        SmallCfg c{pr.nt, pr.minb, 0, pr.cmax, {0, 0}};
-        // largest nmax (multiple of 16) whose class-less layout fits the budget
-        uint32_t lo = 0, hi = 65520 / 16;
+    const char *only = getenv("SASA_B200_CFGS");   // e.g. "0,2,3": restrict the configurations (tuning aid)
+    for (int i = 0; i < kNumProtos; ++i) {
+        const Proto &pr = kProtos[i];
+        if (only && !strchr(only, '0' + i) && i != kNumProtos - 1) continue;
+        const size_t budget = cfg_budget(ctx, pr.minb);
+        SmallCfg c{pr.nt, pr.minb, 0, pr.cmax, {0, 0}, i};
+        uint32_t lo = 0, hi = 65520 / 16;   // largest nmax (multiple of 16) whose class-less layout fits
         while (lo < hi) {
             const uint32_t mid = (lo + hi + 1) / 2;
             if (small_layout(mid * 16, pr.cmax, pr.nt / 32, false).total <= budget) lo = mid;
             else hi = mid - 1;
         }
         c.nmax = lo * 16;
-        if (c.nmax == 0) continue;
+        if (c.nmax == 0) return fail(ctx, SASA_B200_ERR_CUDA, "device shared memory too small for the fused kernel");
         c.smem[0] = small_layout(c.nmax, c.cmax, c.nt / 32, false).total;
-        c.smem[1] = small_layout(c.nmax, c.cmax, c.nt / 32, true).total;
+        c.smem[1] = budget;
+        for (int v = 0; v < 2; ++v) {
+            cudaError_t e = cudaFuncSetAttribute((const void *)pr.fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem[v]);
+            if (e != cudaSuccess)
+                return fail(ctx, SASA_B200_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", c.smem[v], cudaGetErrorString(e));
+        }
         ctx->cfgs.push_back(c);
     }
-    if (ctx->cfgs.size() != 3) return fail(ctx, SASA_B200_ERR_CUDA, "device shared memory too small for the fused kernel");
-    // with id classes the same nmax needs 4 more bytes per atom; the 1-CTA/SM config is capped by the opt-in limit
-    for (SmallCfg &c : ctx->cfgs) {
-        while (c.smem[1] > std::min<size_t>(ctx->smem_optin, (228 * 1024) / c.minb - 1024) && c.nmax > 16) {
-            // shrink only the class-carrying variant by lowering its usable nmax: handled at bucket time
-            break;
-        }
-    }
-    cudaError_t e;
-    if ((e = set_smem_attr<256, 3>(ctx->cfgs[0].smem[0], std::min(ctx->cfgs[0].smem[1], ctx->smem_optin))) != cudaSuccess ||
-        (e = set_smem_attr<256, 2>(ctx->cfgs[1].smem[0], std::min(ctx->cfgs[1].smem[1], ctx->smem_optin))) != cudaSuccess ||
-        (e = set_smem_attr<512, 1>(ctx->cfgs[2].smem[0], std::min(ctx->cfgs[2].smem[1], ctx->smem_optin))) != cudaSuccess)
-        return fail(ctx, SASA_B200_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s", cudaGetErrorString(e));
     return SASA_B200_OK;
 }
 
 // With id classes every atom costs 4 more bytes of shared memory: the atom capacity of a config shrinks.
 uint32_t cfg_capacity(const sasa_b200_ctx *ctx, const SmallCfg &c, bool has_cls) {
     if (!has_cls) return c.nmax;
-    const size_t budget = std::min<size_t>(ctx->smem_optin, (228 * 1024) / c.minb - 1024);
+    const size_t budget = cfg_budget(ctx, c.minb);
     uint32_t n = c.nmax;
     while (n > 0 && small_layout(n, c.cmax, c.nt / 32, true).total > budget) n -= 16;
     return n;
@@ -312,6 +304,11 @@ int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
         return e ? (float)atof(e) : 3.0f;
     }();
     kp->near2 = near_a * near_a;
+    static const int bcast_min = [] {
+        const char *e = getenv("SASA_B200_BCAST_MIN");
+        return e ? atoi(e) : 9;
+    }();
+    kp->bcast_min = bcast_min;
     kp->flags = ra.prm.flags;
     kp->err_flag = ctx->d_err;
     kp->stat = ctx->d_stat;
@@ -350,10 +347,8 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
         kp.cmax = c.cmax;
         const size_t smem = small_layout(kp.nmax, kp.cmax, c.nt / 32, has_cls).total;
         const int grid = (int)std::min<uint32_t>(L.n_work, (uint32_t)(ctx->sm_count * c.minb));
-        cudaError_t e;
-        if (c.nt == 256 && c.minb == 3) e = launch_small<256, 3>(kp, has_cls, grid, smem, st);
-        else if (c.nt == 256 && c.minb == 2) e = launch_small<256, 2>(kp, has_cls, grid, smem, st);
-        else e = launch_small<512, 1>(kp, has_cls, grid, smem, st);
+        void *args[] = {(void *)&kp};
+        cudaError_t e = cudaLaunchKernel((const void *)kProtos[c.proto].fn[has_cls ? 1 : 0], dim3(grid), dim3(c.nt), args, smem, st);
         if (e != cudaSuccess) return fail(ctx, SASA_B200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
         ++*launches;
     }

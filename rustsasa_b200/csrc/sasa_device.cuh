@@ -43,6 +43,7 @@ struct KParams {
     uint32_t n_points, n_body;
     float inv_n, probe;
     float near2;                  // squared centre distance below which a neighbour is "near"
+    int bcast_min;                // survivors needed for the broadcast form of phase 2
     // shared-memory capacities of this launch
     uint32_t nmax, cmax;
     uint32_t flags;
@@ -288,109 +289,136 @@ __device__ __forceinline__ int build_entries(const KParams &p, const AtomAcc &at
     return nfront;
 }
 
-// Phase 1: all points of one 128-point chunk against entries [0, m): one broadcast LDS.128 per neighbour,
-// NBODY pure-body slots (+ NMIX slots that may hold tail points) per lane.
-template <int NBODY, int NMIX>
-__device__ __forceinline__ void phase1(const float4 *ent, int m, const float (&sx)[4], const float (&sy)[4],
-                                       const float (&sz)[4], const bool (&tail)[4], bool (&occ)[4]) {
+// One 128-point chunk of sphere points held in registers: slot s of a lane is point p0 + 32*s + lane.
+struct PointChunk {
+    float sx[4], sy[4], sz[4];
+};
+
+__device__ __forceinline__ void load_chunk(const KParams &p, uint32_t p0, PointChunk &c) {
+    const int lane = lane_id();
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const uint32_t pi = p0 + 32u * s + lane;
+        const bool valid = pi < p.n_points;
+        c.sx[s] = valid ? __ldg(p.px + pi) : 0.0f;
+        c.sy[s] = valid ? __ldg(p.py + pi) : 0.0f;
+        c.sz[s] = valid ? __ldg(p.pz + pi) : 0.0f;
+    }
+}
+
+// Phase 1: all points of one 128-point chunk against entries [0, m): one broadcast LDS.128 per neighbour.
+// Per lane: NB slots that lie wholly in the SIMD body, then NM slots that straddle the body/tail border
+// (evaluated per lane), then NT slots that hold only tail points.
+template <int NB, int NM, int NT>
+__device__ __forceinline__ void phase1(const float4 *ent, int m, const PointChunk &c, const bool (&tail)[4],
+                                       bool (&occ)[4]) {
 #pragma unroll 2
     for (int q = 0; q < m; ++q) {
         const float4 e = ent[q];
 #pragma unroll
-        for (int s = 0; s < NBODY; ++s) occ[s] = occ[s] || (dot_body(sx[s], sy[s], sz[s], e) < e.w);
+        for (int s = 0; s < NB; ++s) occ[s] = occ[s] || (dot_body(c.sx[s], c.sy[s], c.sz[s], e) < e.w);
 #pragma unroll
-        for (int s = NBODY; s < NBODY + NMIX; ++s) occ[s] = occ[s] || occl(sx[s], sy[s], sz[s], tail[s], e);
+        for (int s = NB; s < NB + NM; ++s) occ[s] = occ[s] || occl(c.sx[s], c.sy[s], c.sz[s], tail[s], e);
+#pragma unroll
+        for (int s = NB + NM; s < NB + NM + NT; ++s) occ[s] = occ[s] || (dot_tail(c.sx[s], c.sy[s], c.sz[s], e) <= e.w);
     }
 }
 
-// Phase 2 (few survivors): lanes run over the remaining entries [m, k), one surviving point at a time.
-__device__ __forceinline__ bool survivor_vs_entries(const float4 *ent, int m, int k, float sx, float sy, float sz,
-                                                    bool tail) {
+// Phase 2, few survivors: lanes run over the remaining entries [m, k), one surviving point at a time.
+template <bool TAIL>
+__device__ __forceinline__ bool survivor_vs_entries(const float4 *ent, int m, int k, float sx, float sy, float sz) {
     bool hit = false;
     for (int q = m + lane_id(); q < k; q += 32) {
         const float4 e = ent[q];
-        hit = hit || occl(sx, sy, sz, tail, e);
+        hit = hit || (TAIL ? (dot_tail(sx, sy, sz, e) <= e.w) : (dot_body(sx, sy, sz, e) < e.w));
     }
     return __any_sync(kFull, hit);
 }
 
 // Fast evaluation of one atom whose complete neighbour list sits in ent[0, k) with nfront near entries first.
-// `queue` is per-warp scratch for survivor point indices (kNbCap u16, may alias cand).
-__device__ float atom_fast(const KParams &p, const float4 *ent, int k, int nfront, uint16_t *queue) {
+// `queue` is per-warp scratch for survivor point indices (kNbCap u16, may alias the candidate list).
+// `pre` holds the points of chunk 0 when n_points <= 128 (loaded once per warp, not once per atom).
+__device__ __forceinline__ float atom_fast(const KParams &p, const float4 *ent, int k, int nfront, uint16_t *queue,
+                                           const PointChunk &pre) {
     const int lane = lane_id();
     float exposed = 0.0f;
-    int m = min(k, min(max(nfront, 4), 16));
+    const int m = min(k, min(max(nfront, 4), 16));
+    const bool single = p.n_points <= 128;
     for (uint32_t p0 = 0; p0 < p.n_points; p0 += 128) {
-        float sx[4], sy[4], sz[4];
+        PointChunk c = pre;
+        if (!single) load_chunk(p, p0, c);
         bool occ[4], tail[4];
         const uint32_t rem = p.n_points - p0;
         const int nslots = rem >= 128 ? 4 : (int)((rem + 31) >> 5);
-        // slots wholly inside the SIMD body; every other used slot is evaluated per lane
-        int nbody = 0;
+        int nb = 0, nt = 0;   // pure-body and pure-tail slots of this chunk
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             const uint32_t pi = p0 + 32u * s + lane;
-            const bool valid = pi < p.n_points;
-            sx[s] = valid ? __ldg(p.px + pi) : 0.0f;
-            sy[s] = valid ? __ldg(p.py + pi) : 0.0f;
-            sz[s] = valid ? __ldg(p.pz + pi) : 0.0f;
-            occ[s] = !valid;
+            occ[s] = pi >= p.n_points;
             tail[s] = pi >= p.n_body;
-            if (p0 + 32u * s + 32u <= p.n_body) nbody = s + 1;
+            if (p0 + 32u * s + 32u <= p.n_body) nb = s + 1;
+            if (s < nslots && p0 + 32u * s >= p.n_body) ++nt;
         }
-        const int nmix = nslots - nbody;
-        if (nbody == 4) phase1<4, 0>(ent, m, sx, sy, sz, tail, occ);
-        else if (nbody == 3 && nmix == 1) phase1<3, 1>(ent, m, sx, sy, sz, tail, occ);
-        else if (nbody == 3) phase1<3, 0>(ent, m, sx, sy, sz, tail, occ);
-        else if (nbody == 2 && nmix == 0) phase1<2, 0>(ent, m, sx, sy, sz, tail, occ);
-        else if (nbody == 1 && nmix == 0) phase1<1, 0>(ent, m, sx, sy, sz, tail, occ);
-        else phase1<0, 4>(ent, m, sx, sy, sz, tail, occ);
+        const int nm = nslots - nb - nt;
+        if (nb == 4) phase1<4, 0, 0>(ent, m, c, tail, occ);
+        else if (nb == 3 && nm == 0 && nt == 1) phase1<3, 0, 1>(ent, m, c, tail, occ);
+        else if (nb == 3 && nm == 0 && nt == 0) phase1<3, 0, 0>(ent, m, c, tail, occ);
+        else if (nb == 2 && nm == 0 && nt == 0) phase1<2, 0, 0>(ent, m, c, tail, occ);
+        else if (nb == 1 && nm == 0 && nt == 0) phase1<1, 0, 0>(ent, m, c, tail, occ);
+        else phase1<0, 4, 0>(ent, m, c, tail, occ);
         if (m == k) {
 #pragma unroll
             for (int s = 0; s < 4; ++s) exposed += (float)__popc(__ballot_sync(kFull, !occ[s]));
             continue;
         }
-        // survivors -> queue (slot-major order)
-        int ns = 0;
+        // survivors -> queue: body points from the front, tail points from the back
+        int nsb = 0, nst = 0;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
-            const unsigned ms = __ballot_sync(kFull, !occ[s]);
-            if (!occ[s]) queue[ns + __popc(ms & lanemask_lt())] = (uint16_t)(32 * s + lane);
-            ns += __popc(ms);
+            const unsigned mb = __ballot_sync(kFull, !occ[s] && !tail[s]);
+            const unsigned mt = __ballot_sync(kFull, !occ[s] && tail[s]);
+            if (!occ[s]) {
+                const int at = tail[s] ? (kNbCap - 1) - (nst + __popc(mt & lanemask_lt())) : nsb + __popc(mb & lanemask_lt());
+                queue[at] = (uint16_t)(32 * s + lane);
+            }
+            nsb += __popc(mb);
+            nst += __popc(mt);
         }
         __syncwarp();
-        if (ns == 0) continue;
-        if (ns >= 12) {
-            // many survivors: one survivor per lane, broadcast the remaining entries
-            for (int b = 0; b < ns; b += 32) {
-                const bool have = b + lane < ns;
+        if (nsb >= p.bcast_min) {
+            // many survivors: one survivor per lane, broadcast the remaining entries, leave when all are dead
+            for (int b = 0; b < nsb; b += 32) {
+                const bool have = b + lane < nsb;
                 const uint32_t pi = p0 + (have ? (uint32_t)queue[b + lane] : 0u);
                 const float qx = __ldg(p.px + pi), qy = __ldg(p.py + pi), qz = __ldg(p.pz + pi);
-                const bool qt = pi >= p.n_body;
                 bool dead = !have;
-                const bool any_tail = __any_sync(kFull, have && qt);
-                if (!any_tail) {
-                    for (int q = m; q < k; ++q) {
+                int q = m;
+                for (; q + 4 <= k; q += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 e = ent[q + u];
+                        dead = dead || (dot_body(qx, qy, qz, e) < e.w);
+                    }
+                    if (__all_sync(kFull, dead)) break;
+                }
+                if (q + 4 > k)
+                    for (; q < k; ++q) {
                         const float4 e = ent[q];
                         dead = dead || (dot_body(qx, qy, qz, e) < e.w);
-                        if ((q & 3) == 3 && __all_sync(kFull, dead)) break;
                     }
-                } else {
-                    for (int q = m; q < k; ++q) {
-                        const float4 e = ent[q];
-                        dead = dead || occl(qx, qy, qz, qt, e);
-                        if ((q & 3) == 3 && __all_sync(kFull, dead)) break;
-                    }
-                }
                 exposed += (float)__popc(__ballot_sync(kFull, !dead));
             }
         } else {
-            // few survivors: lanes over entries, one survivor at a time
-            for (int t = 0; t < ns; ++t) {
+            for (int t = 0; t < nsb; ++t) {
                 const uint32_t pi = p0 + (uint32_t)queue[t];
-                const float qx = __ldg(p.px + pi), qy = __ldg(p.py + pi), qz = __ldg(p.pz + pi);
-                if (!survivor_vs_entries(ent, m, k, qx, qy, qz, pi >= p.n_body)) exposed += 1.0f;
+                if (!survivor_vs_entries<false>(ent, m, k, __ldg(p.px + pi), __ldg(p.py + pi), __ldg(p.pz + pi)))
+                    exposed += 1.0f;
             }
+        }
+        for (int t = 0; t < nst; ++t) {
+            const uint32_t pi = p0 + (uint32_t)queue[kNbCap - 1 - t];
+            if (!survivor_vs_entries<true>(ent, m, k, __ldg(p.px + pi), __ldg(p.py + pi), __ldg(p.pz + pi)))
+                exposed += 1.0f;
         }
         __syncwarp();
     }

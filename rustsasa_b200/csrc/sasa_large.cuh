@@ -232,6 +232,8 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
     const GlobalAtoms atoms{sorted};
     const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0;
     unsigned long long pairs = 0, streamed = 0;
+    PointChunk pre;
+    load_chunk(p, 0, pre);
     for (;;) {
         unsigned pos_u = 0;
         if (lane == 0) pos_u = atomicAdd(&h->next_atom, 1u);
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
         if (k >= 0) {
             const float r = __fadd_rn(ai.w, p.probe);
             const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
-            cnt = atom_fast(p, w_ent, k, nfront, reinterpret_cast<uint16_t *>(w_cand));
+            cnt = atom_fast(p, w_ent, k, nfront, reinterpret_cast<uint16_t *>(w_cand), pre);
             pairs += (unsigned)k;
         } else {
             cnt = stats ? atom_streaming<GlobalAtoms, uint32_t, true>(p, g, atoms, cells, cls_sorted, pos, w_ent, p.stat)

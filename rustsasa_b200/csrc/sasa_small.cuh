@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
     float4 *w_ent = s_ent + warp * kNbCap;
     uint16_t *w_cand = s_cand + warp * kNbCap;
     const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0;
+    PointChunk pre;
+    load_chunk(p, 0, pre);
 
     for (;;) {
         __syncthreads();
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
             if (k >= 0) {
                 const float r = __fadd_rn(ai.w, p.probe);
                 const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
-                cnt = atom_fast(p, w_ent, k, nfront, w_cand);
+                cnt = atom_fast(p, w_ent, k, nfront, w_cand, pre);
                 pairs += (unsigned)k;
             } else {
                 cnt = stats ? atom_streaming<SmemAtoms, uint16_t, true>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat)
