@@ -127,8 +127,8 @@ struct Proto {
 };
 #define SASA_PROTO(NT, MINB, CMAX) \
     Proto { NT, MINB, CMAX, { sasa_small_kernel<NT, MINB, false>, sasa_small_kernel<NT, MINB, true> } }
-const Proto kProtos[] = {SASA_PROTO(256, 3, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(256, 2, 8192),
-                         SASA_PROTO(512, 1, 16384)};
+// every configuration keeps 32 warps resident per SM (64 registers/thread)
+const Proto kProtos[] = {SASA_PROTO(256, 4, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384)};
 constexpr int kNumProtos = sizeof(kProtos) / sizeof(kProtos[0]);
 
 size_t cfg_budget(const sasa_b200_ctx *ctx, int minb) {
@@ -301,14 +301,18 @@ int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
     kp->probe = ra.prm.probe_radius;
     static const float near_a = [] {
         const char *e = getenv("SASA_B200_NEAR");
-        return e ? (float)atof(e) : 3.0f;
+        return e ? (float)atof(e) : 4.0f;
     }();
     kp->near2 = near_a * near_a;
     static const int bcast_min = [] {
         const char *e = getenv("SASA_B200_BCAST_MIN");
-        return e ? atoi(e) : 9;
+        return e ? atoi(e) : 6;
     }();
     kp->bcast_min = bcast_min;
+    static const int m_min = [] { const char *e = getenv("SASA_B200_M_MIN"); return e ? atoi(e) : 4; }();
+    static const int m_max = [] { const char *e = getenv("SASA_B200_M_MAX"); return e ? atoi(e) : 16; }();
+    kp->m_min = m_min;
+    kp->m_max = m_max;
     kp->flags = ra.prm.flags;
     kp->err_flag = ctx->d_err;
     kp->stat = ctx->d_stat;

@@ -17,7 +17,8 @@ namespace sasa {
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kNbCap = 128;           // neighbour entries staged per warp
+constexpr int kNbCap = 96;            // neighbour entries staged per warp (protein lists peak around 75)
+constexpr int kQueueCap = 128;        // survivor queue of one 128-point chunk (u16 per warp; aliases the candidate list)
 constexpr float kCutSlack = 1.0e-3f;  // Angstrom; keeps exactly-tangent pairs in the list
 constexpr float kCellSafety = 1.0002f;
 constexpr double kBoundaryTol = 1.0e-5;
@@ -44,6 +45,7 @@ struct KParams {
     float inv_n, probe;
     float near2;                  // squared centre distance below which a neighbour is "near"
     int bcast_min;                // survivors needed for the broadcast form of phase 2
+    int m_min, m_max;             // bounds on the number of entries phase 1 tests against every point
     // shared-memory capacities of this launch
     uint32_t nmax, cmax;
     uint32_t flags;
@@ -306,6 +308,13 @@ __device__ __forceinline__ void load_chunk(const KParams &p, uint32_t p0, PointC
     }
 }
 
+// A single sphere point by index: from the per-CTA float4 table when the whole point set fits it
+// (n_points <= 128), else from the global SoA arrays through L1.
+__device__ __forceinline__ float4 point_at(const KParams &p, const float4 *s_pts, uint32_t pi) {
+    if (s_pts) return s_pts[pi];
+    return make_float4(__ldg(p.px + pi), __ldg(p.py + pi), __ldg(p.pz + pi), 0.0f);
+}
+
 // Phase 1: all points of one 128-point chunk against entries [0, m): one broadcast LDS.128 per neighbour.
 // Per lane: NB slots that lie wholly in the SIMD body, then NM slots that straddle the body/tail border
 // (evaluated per lane), then NT slots that hold only tail points.
@@ -336,13 +345,13 @@ __device__ __forceinline__ bool survivor_vs_entries(const float4 *ent, int m, in
 }
 
 // Fast evaluation of one atom whose complete neighbour list sits in ent[0, k) with nfront near entries first.
-// `queue` is per-warp scratch for survivor point indices (kNbCap u16, may alias the candidate list).
+// `queue` is per-warp scratch for survivor point indices (kQueueCap u16, may alias the candidate list).
 // `pre` holds the points of chunk 0 when n_points <= 128 (loaded once per warp, not once per atom).
 __device__ __forceinline__ float atom_fast(const KParams &p, const float4 *ent, int k, int nfront, uint16_t *queue,
-                                           const PointChunk &pre) {
+                                           const PointChunk &pre, const float4 *s_pts) {
     const int lane = lane_id();
     float exposed = 0.0f;
-    const int m = min(k, min(max(nfront, 4), 16));
+    const int m = min(k, min(max(nfront, p.m_min), p.m_max));
     const bool single = p.n_points <= 128;
     for (uint32_t p0 = 0; p0 < p.n_points; p0 += 128) {
         PointChunk c = pre;
@@ -378,7 +387,7 @@ __device__ __forceinline__ float atom_fast(const KParams &p, const float4 *ent, 
             const unsigned mb = __ballot_sync(kFull, !occ[s] && !tail[s]);
             const unsigned mt = __ballot_sync(kFull, !occ[s] && tail[s]);
             if (!occ[s]) {
-                const int at = tail[s] ? (kNbCap - 1) - (nst + __popc(mt & lanemask_lt())) : nsb + __popc(mb & lanemask_lt());
+                const int at = tail[s] ? (kQueueCap - 1) - (nst + __popc(mt & lanemask_lt())) : nsb + __popc(mb & lanemask_lt());
                 queue[at] = (uint16_t)(32 * s + lane);
             }
             nsb += __popc(mb);
@@ -390,7 +399,8 @@ __device__ __forceinline__ float atom_fast(const KParams &p, const float4 *ent, 
             for (int b = 0; b < nsb; b += 32) {
                 const bool have = b + lane < nsb;
                 const uint32_t pi = p0 + (have ? (uint32_t)queue[b + lane] : 0u);
-                const float qx = __ldg(p.px + pi), qy = __ldg(p.py + pi), qz = __ldg(p.pz + pi);
+                const float4 pt = point_at(p, s_pts, pi);
+                const float qx = pt.x, qy = pt.y, qz = pt.z;
                 bool dead = !have;
                 int q = m;
                 for (; q + 4 <= k; q += 4) {
@@ -410,15 +420,13 @@ __device__ __forceinline__ float atom_fast(const KParams &p, const float4 *ent, 
             }
         } else {
             for (int t = 0; t < nsb; ++t) {
-                const uint32_t pi = p0 + (uint32_t)queue[t];
-                if (!survivor_vs_entries<false>(ent, m, k, __ldg(p.px + pi), __ldg(p.py + pi), __ldg(p.pz + pi)))
-                    exposed += 1.0f;
+                const float4 pt = point_at(p, s_pts, p0 + (uint32_t)queue[t]);
+                if (!survivor_vs_entries<false>(ent, m, k, pt.x, pt.y, pt.z)) exposed += 1.0f;
             }
         }
         for (int t = 0; t < nst; ++t) {
-            const uint32_t pi = p0 + (uint32_t)queue[kNbCap - 1 - t];
-            if (!survivor_vs_entries<true>(ent, m, k, __ldg(p.px + pi), __ldg(p.py + pi), __ldg(p.pz + pi)))
-                exposed += 1.0f;
+            const float4 pt = point_at(p, s_pts, p0 + (uint32_t)queue[kQueueCap - 1 - t]);
+            if (!survivor_vs_entries<true>(ent, m, k, pt.x, pt.y, pt.z)) exposed += 1.0f;
         }
         __syncwarp();
     }

@@ -223,7 +223,9 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
                                                              const uint32_t *__restrict__ cls_sorted, const uint32_t *__restrict__ cells,
                                                              float *val) {
     __shared__ __align__(16) float4 s_ent[8 * kNbCap];
-    __shared__ uint32_t s_cand[8 * kNbCap];
+    __shared__ uint32_t s_cand[8 * kNbCap];       // u32 candidate positions; reused as the u16 survivor queue
+    static_assert(kNbCap * 2 >= kQueueCap, "survivor queue must fit the candidate list");
+    __shared__ __align__(16) float4 s_ptab[128];
     if (h->ncell == 0) return;
     const Grid g = h->grid;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -234,6 +236,13 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
     unsigned long long pairs = 0, streamed = 0;
     PointChunk pre;
     load_chunk(p, 0, pre);
+    const float4 *s_pts = p.n_points <= 128 ? s_ptab : nullptr;
+    if (threadIdx.x < 128) {
+        const bool v = threadIdx.x < p.n_points;
+        s_ptab[threadIdx.x] = make_float4(v ? __ldg(p.px + threadIdx.x) : 0.f, v ? __ldg(p.py + threadIdx.x) : 0.f,
+                                          v ? __ldg(p.pz + threadIdx.x) : 0.f, 0.f);
+    }
+    __syncthreads();
     for (;;) {
         unsigned pos_u = 0;
         if (lane == 0) pos_u = atomicAdd(&h->next_atom, 1u);
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
         if (k >= 0) {
             const float r = __fadd_rn(ai.w, p.probe);
             const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
-            cnt = atom_fast(p, w_ent, k, nfront, reinterpret_cast<uint16_t *>(w_cand), pre);
+            cnt = atom_fast(p, w_ent, k, nfront, reinterpret_cast<uint16_t *>(w_cand), pre, s_pts);
             pairs += (unsigned)k;
         } else {
             cnt = stats ? atom_streaming<GlobalAtoms, uint32_t, true>(p, g, atoms, cells, cls_sorted, pos, w_ent, p.stat)

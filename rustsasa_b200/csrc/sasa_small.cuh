@@ -20,7 +20,7 @@ struct SmemAtoms {
 };
 
 struct SmallLayout {
-    size_t atom, ent, val, cls, cellw, red, misc, orig, cand, total;
+    size_t atom, ent, pts, val, cls, cellw, red, misc, orig, cand, total;
 };
 
 __host__ __device__ inline SmallLayout small_layout(uint32_t nmax, uint32_t cmax, int nwarps, bool has_cls) {
@@ -28,13 +28,14 @@ __host__ __device__ inline SmallLayout small_layout(uint32_t nmax, uint32_t cmax
     size_t o = 0;
     L.atom = o;  o += (size_t)nmax * 16;
     L.ent = o;   o += (size_t)nwarps * kNbCap * 16;
+    L.pts = o;   o += 128 * 16;
     L.val = o;   o += (size_t)nmax * 4;
     L.cls = o;   o += has_cls ? (size_t)nmax * 4 : 0;
     L.cellw = o; o += (((size_t)cmax + 2 + 1) / 2) * 4;
     L.red = o;   o += 32 * 8 * 4;
     L.misc = o;  o += 64;
     L.orig = o;  o += (size_t)nmax * 2;
-    L.cand = o;  o += (size_t)nwarps * kNbCap * 2;
+    L.cand = o;  o += (size_t)nwarps * kQueueCap * 2;
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
     const SmallLayout L = small_layout(p.nmax, p.cmax, NW, HAS_CLS);
     float4 *s_atom = reinterpret_cast<float4 *>(smem + L.atom);
     float4 *s_ent = reinterpret_cast<float4 *>(smem + L.ent);
+    float4 *s_ptab = reinterpret_cast<float4 *>(smem + L.pts);
     float *s_val = reinterpret_cast<float *>(smem + L.val);
     uint16_t *s_cellid = reinterpret_cast<uint16_t *>(smem + L.val);  // aliases s_val during the sort
     uint16_t *s_rank = s_cellid + p.nmax;
@@ -76,10 +78,16 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float4 *w_ent = s_ent + warp * kNbCap;
-    uint16_t *w_cand = s_cand + warp * kNbCap;
+    uint16_t *w_cand = s_cand + warp * kQueueCap;
     const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0;
     PointChunk pre;
     load_chunk(p, 0, pre);
+    // the whole point set as a float4 table when it fits (n_points <= 128): phase 2 fetches survivors from it
+    const float4 *s_pts = p.n_points <= 128 ? s_ptab : nullptr;
+    if (tid < 128) {
+        const bool v = (uint32_t)tid < p.n_points;
+        s_ptab[tid] = make_float4(v ? __ldg(p.px + tid) : 0.f, v ? __ldg(p.py + tid) : 0.f, v ? __ldg(p.pz + tid) : 0.f, 0.f);
+    }
 
     for (;;) {
         __syncthreads();
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
             if (k >= 0) {
                 const float r = __fadd_rn(ai.w, p.probe);
                 const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
-                cnt = atom_fast(p, w_ent, k, nfront, w_cand, pre);
+                cnt = atom_fast(p, w_ent, k, nfront, w_cand, pre, s_pts);
                 pairs += (unsigned)k;
             } else {
                 cnt = stats ? atom_streaming<SmemAtoms, uint16_t, true>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat)
