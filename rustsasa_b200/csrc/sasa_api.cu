@@ -306,7 +306,7 @@ int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
     kp->near2 = near_a * near_a;
     static const int bcast_min = [] {
         const char *e = getenv("SASA_B200_BCAST_MIN");
-        return e ? atoi(e) : 6;
+        return e ? atoi(e) : 16;
     }();
     kp->bcast_min = bcast_min;
     static const int m_min = [] { const char *e = getenv("SASA_B200_M_MIN"); return e ? atoi(e) : 4; }();

@@ -315,122 +315,118 @@ __device__ __forceinline__ float4 point_at(const KParams &p, const float4 *s_pts
     return make_float4(__ldg(p.px + pi), __ldg(p.py + pi), __ldg(p.pz + pi), 0.0f);
 }
 
-// Phase 1: all points of one 128-point chunk against entries [0, m): one broadcast LDS.128 per neighbour.
-// Per lane: NB slots that lie wholly in the SIMD body, then NM slots that straddle the body/tail border
-// (evaluated per lane), then NT slots that hold only tail points.
-template <int NB, int NM, int NT>
-__device__ __forceinline__ void phase1(const float4 *ent, int m, const PointChunk &c, const bool (&tail)[4],
-                                       bool (&occ)[4]) {
+// Phase 1: the body points of one 128-point chunk (NS slots per lane) against entries [0, m): one broadcast
+// LDS.128 per neighbour, 4 FP32-pipe instructions per point-neighbour test.
+template <int NS>
+__device__ __forceinline__ void phase1(const float4 *ent, int m, const PointChunk &c, bool (&occ)[4]) {
 #pragma unroll 2
     for (int q = 0; q < m; ++q) {
         const float4 e = ent[q];
 #pragma unroll
-        for (int s = 0; s < NB; ++s) occ[s] = occ[s] || (dot_body(c.sx[s], c.sy[s], c.sz[s], e) < e.w);
-#pragma unroll
-        for (int s = NB; s < NB + NM; ++s) occ[s] = occ[s] || occl(c.sx[s], c.sy[s], c.sz[s], tail[s], e);
-#pragma unroll
-        for (int s = NB + NM; s < NB + NM + NT; ++s) occ[s] = occ[s] || (dot_tail(c.sx[s], c.sy[s], c.sz[s], e) <= e.w);
+        for (int s = 0; s < NS; ++s) occ[s] = occ[s] || (dot_body(c.sx[s], c.sy[s], c.sz[s], e) < e.w);
     }
 }
 
-// Phase 2, few survivors: lanes run over the remaining entries [m, k), one surviving point at a time.
+// Phase 2: `ns` (<= 32) surviving points, listed in queue[0, ns), against entries [q0, k) as a 2-D tile:
+// with G = the power of two >= ns, lane l owns survivor (l mod G) and entry offset (l div G), so one
+// step tests 32/G entries against every survivor (ns = 32: one entry broadcast per step; ns = 1: 32 entries
+// per step for the single survivor).  Returns the number of survivors no entry occludes.
 template <bool TAIL>
-__device__ __forceinline__ bool survivor_vs_entries(const float4 *ent, int m, int k, float sx, float sy, float sz) {
+__device__ __forceinline__ int phase2_tile(const KParams &p, const float4 *s_pts, const float4 *ent, int q0, int k,
+                                           const uint16_t *queue, int ns, uint32_t p0) {
+    const int lane = lane_id();
+    int g = 1, sh = 0;
+    while (g < ns) { g <<= 1; ++sh; }
+    const int sidx = lane & (g - 1), eoff = lane >> sh, estep = 32 >> sh;
+    const bool have = sidx < ns;
+    const float4 pt = point_at(p, s_pts, p0 + (have ? (uint32_t)queue[sidx] : 0u));
     bool hit = false;
-    for (int q = m + lane_id(); q < k; q += 32) {
+    for (int q = q0 + eoff; q < k; q += estep) {
         const float4 e = ent[q];
-        hit = hit || (TAIL ? (dot_tail(sx, sy, sz, e) <= e.w) : (dot_body(sx, sy, sz, e) < e.w));
+        hit = hit || (TAIL ? (dot_tail(pt.x, pt.y, pt.z, e) <= e.w) : (dot_body(pt.x, pt.y, pt.z, e) < e.w));
     }
-    return __any_sync(kFull, hit);
+    unsigned mk = __ballot_sync(kFull, hit);
+    for (int st = 16; st >= g; st >>= 1) mk |= mk >> st;     // OR over the lanes that share a survivor
+    const unsigned valid = ns >= 32 ? 0xffffffffu : ((1u << ns) - 1u);
+    return __popc(~mk & valid);
+}
+
+// Broadcast form with early exit for many survivors (G = 32): leaves as soon as every survivor is occluded.
+__device__ __forceinline__ int phase2_bcast(const KParams &p, const float4 *s_pts, const float4 *ent, int q0, int k,
+                                            const uint16_t *queue, int ns, uint32_t p0) {
+    const int lane = lane_id();
+    const bool have = lane < ns;
+    const float4 pt = point_at(p, s_pts, p0 + (have ? (uint32_t)queue[lane] : 0u));
+    bool dead = !have;
+    int q = q0;
+    for (; q + 4 <= k; q += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 e = ent[q + u];
+            dead = dead || (dot_body(pt.x, pt.y, pt.z, e) < e.w);
+        }
+        if (__all_sync(kFull, dead)) return 0;
+    }
+    for (; q < k; ++q) {
+        const float4 e = ent[q];
+        dead = dead || (dot_body(pt.x, pt.y, pt.z, e) < e.w);
+    }
+    return __popc(__ballot_sync(kFull, !dead));
 }
 
 // Fast evaluation of one atom whose complete neighbour list sits in ent[0, k) with nfront near entries first.
-// `queue` is per-warp scratch for survivor point indices (kQueueCap u16, may alias the candidate list).
+// `queue` is per-warp scratch for point indices (kQueueCap u16, may alias the candidate list).
 // `pre` holds the points of chunk 0 when n_points <= 128 (loaded once per warp, not once per atom).
+// Body points (index < n_body) go through phase 1 (first m entries, all points) and phase 2 (survivors, the
+// remaining entries); the few tail points skip phase 1 and are tested against all entries by the tile routine.
 __device__ __forceinline__ float atom_fast(const KParams &p, const float4 *ent, int k, int nfront, uint16_t *queue,
                                            const PointChunk &pre, const float4 *s_pts) {
     const int lane = lane_id();
-    float exposed = 0.0f;
+    int exposed = 0;
     const int m = min(k, min(max(nfront, p.m_min), p.m_max));
     const bool single = p.n_points <= 128;
     for (uint32_t p0 = 0; p0 < p.n_points; p0 += 128) {
         PointChunk c = pre;
         if (!single) load_chunk(p, p0, c);
-        bool occ[4], tail[4];
-        const uint32_t rem = p.n_points - p0;
-        const int nslots = rem >= 128 ? 4 : (int)((rem + 31) >> 5);
-        int nb = 0, nt = 0;   // pure-body and pure-tail slots of this chunk
+        const uint32_t pend = min(p0 + 128u, p.n_points);
+        const uint32_t bend = min(pend, max(p.n_body, p0));      // body points of the chunk: [p0, bend)
+        const int nsl = (int)((bend - p0 + 31u) >> 5);           // slots holding at least one body point
+        bool occ[4];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const uint32_t pi = p0 + 32u * s + lane;
-            occ[s] = pi >= p.n_points;
-            tail[s] = pi >= p.n_body;
-            if (p0 + 32u * s + 32u <= p.n_body) nb = s + 1;
-            if (s < nslots && p0 + 32u * s >= p.n_body) ++nt;
-        }
-        const int nm = nslots - nb - nt;
-        if (nb == 4) phase1<4, 0, 0>(ent, m, c, tail, occ);
-        else if (nb == 3 && nm == 0 && nt == 1) phase1<3, 0, 1>(ent, m, c, tail, occ);
-        else if (nb == 3 && nm == 0 && nt == 0) phase1<3, 0, 0>(ent, m, c, tail, occ);
-        else if (nb == 2 && nm == 0 && nt == 0) phase1<2, 0, 0>(ent, m, c, tail, occ);
-        else if (nb == 1 && nm == 0 && nt == 0) phase1<1, 0, 0>(ent, m, c, tail, occ);
-        else phase1<0, 4, 0>(ent, m, c, tail, occ);
+        for (int s = 0; s < 4; ++s) occ[s] = p0 + 32u * s + lane >= bend;
+        if (nsl == 4) phase1<4>(ent, m, c, occ);
+        else if (nsl == 3) phase1<3>(ent, m, c, occ);
+        else if (nsl == 2) phase1<2>(ent, m, c, occ);
+        else if (nsl == 1) phase1<1>(ent, m, c, occ);
         if (m == k) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) exposed += (float)__popc(__ballot_sync(kFull, !occ[s]));
-            continue;
-        }
-        // survivors -> queue: body points from the front, tail points from the back
-        int nsb = 0, nst = 0;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const unsigned mb = __ballot_sync(kFull, !occ[s] && !tail[s]);
-            const unsigned mt = __ballot_sync(kFull, !occ[s] && tail[s]);
-            if (!occ[s]) {
-                const int at = tail[s] ? (kQueueCap - 1) - (nst + __popc(mt & lanemask_lt())) : nsb + __popc(mb & lanemask_lt());
-                queue[at] = (uint16_t)(32 * s + lane);
-            }
-            nsb += __popc(mb);
-            nst += __popc(mt);
-        }
-        __syncwarp();
-        if (nsb >= p.bcast_min) {
-            // many survivors: one survivor per lane, broadcast the remaining entries, leave when all are dead
-            for (int b = 0; b < nsb; b += 32) {
-                const bool have = b + lane < nsb;
-                const uint32_t pi = p0 + (have ? (uint32_t)queue[b + lane] : 0u);
-                const float4 pt = point_at(p, s_pts, pi);
-                const float qx = pt.x, qy = pt.y, qz = pt.z;
-                bool dead = !have;
-                int q = m;
-                for (; q + 4 <= k; q += 4) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float4 e = ent[q + u];
-                        dead = dead || (dot_body(qx, qy, qz, e) < e.w);
-                    }
-                    if (__all_sync(kFull, dead)) break;
-                }
-                if (q + 4 > k)
-                    for (; q < k; ++q) {
-                        const float4 e = ent[q];
-                        dead = dead || (dot_body(qx, qy, qz, e) < e.w);
-                    }
-                exposed += (float)__popc(__ballot_sync(kFull, !dead));
-            }
+            for (int s = 0; s < 4; ++s) exposed += __popc(__ballot_sync(kFull, !occ[s]));
         } else {
-            for (int t = 0; t < nsb; ++t) {
-                const float4 pt = point_at(p, s_pts, p0 + (uint32_t)queue[t]);
-                if (!survivor_vs_entries<false>(ent, m, k, pt.x, pt.y, pt.z)) exposed += 1.0f;
+            int ns = 0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const unsigned mb = __ballot_sync(kFull, !occ[s]);
+                if (!occ[s]) queue[ns + __popc(mb & lanemask_lt())] = (uint16_t)(32 * s + lane);
+                ns += __popc(mb);
             }
+            __syncwarp();
+            for (int b = 0; b < ns; b += 32) {
+                const int nb = min(32, ns - b);
+                exposed += nb > p.bcast_min ? phase2_bcast(p, s_pts, ent, m, k, queue + b, nb, p0)
+                                            : phase2_tile<false>(p, s_pts, ent, m, k, queue + b, nb, p0);
+            }
+            __syncwarp();
         }
-        for (int t = 0; t < nst; ++t) {
-            const float4 pt = point_at(p, s_pts, p0 + (uint32_t)queue[kQueueCap - 1 - t]);
-            if (!survivor_vs_entries<true>(ent, m, k, pt.x, pt.y, pt.z)) exposed += 1.0f;
+        // tail points [bend, pend) of this chunk against every entry
+        for (uint32_t t0 = bend; t0 < pend; t0 += 32) {
+            const int nt = (int)min(32u, pend - t0);
+            if (lane < nt) queue[lane] = (uint16_t)(t0 - p0 + lane);
+            __syncwarp();
+            exposed += k ? phase2_tile<true>(p, s_pts, ent, 0, k, queue, nt, p0) : nt;
+            __syncwarp();
         }
-        __syncwarp();
     }
-    return exposed;
+    return (float)exposed;
 }
 
 }  // namespace sasa
