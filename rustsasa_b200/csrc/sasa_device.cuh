@@ -264,6 +264,68 @@ __device__ __forceinline__ int gather_candidates(const KParams &p, const Grid &g
     return k <= kNbCap ? k : -1;
 }
 
+// Register cache of the flattened candidate list of one cell: window w of lane l is candidate 32*w + l.
+// All atoms of a cell share it, so consecutive atoms of the same cell skip rows_of / row_lookup altogether.
+constexpr int kCacheWin = 12;   // 384 candidates; denser neighbourhoods use the uncached gather
+template <typename IdxT>
+struct CandCache {
+    static constexpr int kPer = sizeof(IdxT) == 2 ? 2 : 1;
+    uint32_t v[kCacheWin / kPer];
+    int total;   // < 0: not cacheable (too many candidates)
+    int cell;
+    __device__ __forceinline__ void set(int w, int j) {
+        if (kPer == 2) v[w >> 1] = (w & 1) ? ((v[w >> 1] & 0xffffu) | ((uint32_t)j << 16)) : ((uint32_t)j & 0xffffu);
+        else v[w] = (uint32_t)j;
+    }
+    __device__ __forceinline__ int get(int w) const {
+        if (kPer == 2) return (int)((w & 1) ? (v[w >> 1] >> 16) : (v[w >> 1] & 0xffffu));
+        return (int)v[w];
+    }
+};
+
+template <typename CellT, typename IdxT>
+__device__ __forceinline__ void fill_cache(const Grid &g, const CellT *cell, int cx, int cy, int cz, int cell_id,
+                                           CandCache<IdxT> &cc) {
+    const Rows rows = rows_of(g, cell, cx, cy, cz);
+    cc.cell = cell_id;
+    cc.total = rows.total <= 32 * kCacheWin ? rows.total : -1;
+    if (cc.total < 0) return;
+#pragma unroll
+    for (int w = 0; w < kCacheWin; ++w)
+        if (32 * w < rows.total) cc.set(w, row_lookup(rows, 32 * w + lane_id()));
+}
+
+// Pass 1 through the cache: same result as gather_candidates.
+template <typename AtomAcc, typename IdxT>
+__device__ __forceinline__ int gather_cached(const KParams &p, const AtomAcc &atoms, const uint32_t *cls_sorted, int pos,
+                                             const float4 ai, const CandCache<IdxT> &cc, IdxT *cand) {
+    const int lane = lane_id();
+    const float reach_i = ai.w + 2.0f * p.probe + kCutSlack;
+    const uint32_t cls_i = cls_sorted ? cls_sorted[pos] : 0u;
+    int k = 0;
+#pragma unroll
+    for (int w = 0; w < kCacheWin; ++w) {
+        if (32 * w >= cc.total) break;
+        const int j = cc.get(w);
+        bool acc = false;
+        if (32 * w + lane < cc.total && j != pos) {
+            const float4 aj = atoms(j);
+            const float dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            const float cut = reach_i + aj.w;
+            acc = d2 <= cut * cut && !(cls_sorted && cls_sorted[j] == cls_i);
+        }
+        const unsigned m = __ballot_sync(kFull, acc);
+        if (m) {
+            const int at = k + __popc(m & lanemask_lt());
+            if (acc && at < kNbCap) cand[at] = (IdxT)j;
+            k += __popc(m);
+        }
+    }
+    __syncwarp();
+    return k <= kNbCap ? k : -1;
+}
+
 // Pass 2: turn candidate positions into (v, limit) entries; "near" neighbours (centre distance^2 < near2) are
 // packed at the front, the rest at the back.  Returns the number of near entries.
 template <typename AtomAcc, typename IdxT>
@@ -319,12 +381,17 @@ __device__ __forceinline__ float4 point_at(const KParams &p, const float4 *s_pts
 // LDS.128 per neighbour, 4 FP32-pipe instructions per point-neighbour test.
 template <int NS>
 __device__ __forceinline__ void phase1(const float4 *ent, int m, const PointChunk &c, bool (&occ)[4]) {
+    // scalar flags (not an array) so that ptxas keeps them in predicate registers: FSETP.LT.OR P, dot, limit, P
+    bool o0 = occ[0], o1 = occ[1], o2 = occ[2], o3 = occ[3];
 #pragma unroll 2
     for (int q = 0; q < m; ++q) {
         const float4 e = ent[q];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) occ[s] = occ[s] || (dot_body(c.sx[s], c.sy[s], c.sz[s], e) < e.w);
+        if (NS > 0) o0 = o0 || (dot_body(c.sx[0], c.sy[0], c.sz[0], e) < e.w);
+        if (NS > 1) o1 = o1 || (dot_body(c.sx[1], c.sy[1], c.sz[1], e) < e.w);
+        if (NS > 2) o2 = o2 || (dot_body(c.sx[2], c.sy[2], c.sz[2], e) < e.w);
+        if (NS > 3) o3 = o3 || (dot_body(c.sx[3], c.sy[3], c.sz[3], e) < e.w);
     }
+    occ[0] = o0; occ[1] = o1; occ[2] = o2; occ[3] = o3;
 }
 
 // Phase 2: `ns` (<= 32) surviving points, listed in queue[0, ns), against entries [q0, k) as a 2-D tile:

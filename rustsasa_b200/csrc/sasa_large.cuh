@@ -243,33 +243,47 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
                                           v ? __ldg(p.pz + threadIdx.x) : 0.f, 0.f);
     }
     __syncthreads();
+    constexpr unsigned kFetch = 4;
+    CandCache<uint32_t> cc;
     for (;;) {
-        unsigned pos_u = 0;
-        if (lane == 0) pos_u = atomicAdd(&h->next_atom, 1u);
-        const int pos = (int)__shfl_sync(kFull, pos_u, 0);
-        if (pos >= N) break;
-        const float4 ai = atoms(pos);
-        float cnt;
-        int k = -1;
-        if (!force_stream && !stats) k = gather_candidates(p, g, atoms, cells, cls_sorted, pos, ai, w_cand);
-        if (k >= 0) {
-            const float r = __fadd_rn(ai.w, p.probe);
-            const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
-            cnt = atom_fast(p, w_ent, k, nfront, reinterpret_cast<uint16_t *>(w_cand), pre, s_pts);
-            pairs += (unsigned)k;
-        } else {
-            cnt = stats ? atom_streaming<GlobalAtoms, uint32_t, true>(p, g, atoms, cells, cls_sorted, pos, w_ent, p.stat)
-                        : atom_streaming<GlobalAtoms, uint32_t, false>(p, g, atoms, cells, cls_sorted, pos, w_ent, p.stat);
-            streamed += 1;
+        unsigned base_u = 0;
+        if (lane == 0) base_u = atomicAdd(&h->next_atom, kFetch);
+        const int base = (int)__shfl_sync(kFull, base_u, 0);
+        if (base >= N) break;
+        cc.cell = -1;
+        cc.total = -1;
+        const int pend = min(base + (int)kFetch, N);
+        for (int pos = base; pos < pend; ++pos) {
+            const float4 ai = atoms(pos);
+            float cnt;
+            int k = -1;
+            if (!force_stream && !stats) {
+                const int cx = cell_coord(ai.x, g.minx, g.inv_c, g.nx), cy = cell_coord(ai.y, g.miny, g.inv_c, g.ny),
+                          cz = cell_coord(ai.z, g.minz, g.inv_c, g.nz);
+                const int cid = (cz * g.ny + cy) * g.nx + cx;
+                if (cid != cc.cell) fill_cache(g, cells, cx, cy, cz, cid, cc);
+                k = cc.total >= 0 ? gather_cached(p, atoms, cls_sorted, pos, ai, cc, w_cand)
+                                  : gather_candidates(p, g, atoms, cells, cls_sorted, pos, ai, w_cand);
+            }
+            if (k >= 0) {
+                const float r = __fadd_rn(ai.w, p.probe);
+                const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
+                cnt = atom_fast(p, w_ent, k, nfront, reinterpret_cast<uint16_t *>(w_cand), pre, s_pts);
+                pairs += (unsigned)k;
+            } else {
+                cnt = stats ? atom_streaming<GlobalAtoms, uint32_t, true>(p, g, atoms, cells, cls_sorted, pos, w_ent, p.stat)
+                            : atom_streaming<GlobalAtoms, uint32_t, false>(p, g, atoms, cells, cls_sorted, pos, w_ent, p.stat);
+                streamed += 1;
+            }
+            if (lane == 0) {
+                const uint32_t oi = orig[pos];
+                const float area = atom_area(ai.w, p.probe, cnt, p.inv_n);
+                val[oi] = area;
+                if (p.out_counts) p.out_counts[a0 + oi] = (uint32_t)cnt;
+                if (p.out_atom) p.out_atom[a0 + oi] = area;
+            }
+            __syncwarp();
         }
-        if (lane == 0) {
-            const uint32_t oi = orig[pos];
-            const float area = atom_area(ai.w, p.probe, cnt, p.inv_n);
-            val[oi] = area;
-            if (p.out_counts) p.out_counts[a0 + oi] = (uint32_t)cnt;
-            if (p.out_atom) p.out_atom[a0 + oi] = area;
-        }
-        __syncwarp();
     }
     if (lane == 0 && p.stat) {
         if (pairs) atomicAdd(p.stat + 1, pairs);

@@ -202,27 +202,41 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
         // ---- per-atom work: warps pull atoms (in cell order) from a shared counter ---------------
         const SmemAtoms atoms{s_atom};
         unsigned long long pairs = 0, streamed = 0;
+        constexpr int kFetch = 4;   // consecutive cell-sorted atoms per fetch: neighbours in the list share cells
+        CandCache<uint16_t> cc;
         for (;;) {
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(&s_misc[1], 1);
-            pos = __shfl_sync(kFull, pos, 0);
-            if (pos >= N) break;
-            const float4 ai = s_atom[pos];
-            float cnt;
-            int k = -1;
-            if (!force_stream && !stats) k = gather_candidates(p, g, atoms, s_cell, s_cls, pos, ai, w_cand);
-            if (k >= 0) {
-                const float r = __fadd_rn(ai.w, p.probe);
-                const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
-                cnt = atom_fast(p, w_ent, k, nfront, w_cand, pre, s_pts);
-                pairs += (unsigned)k;
-            } else {
-                cnt = stats ? atom_streaming<SmemAtoms, uint16_t, true>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat)
-                            : atom_streaming<SmemAtoms, uint16_t, false>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat);
-                streamed += 1;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_misc[1], kFetch);
+            base = __shfl_sync(kFull, base, 0);
+            if (base >= N) break;
+            cc.cell = -1;
+            cc.total = -1;
+            const int pend = min(base + kFetch, N);
+            for (int pos = base; pos < pend; ++pos) {
+                const float4 ai = s_atom[pos];
+                float cnt;
+                int k = -1;
+                if (!force_stream && !stats) {
+                    const int cx = cell_coord(ai.x, g.minx, g.inv_c, g.nx), cy = cell_coord(ai.y, g.miny, g.inv_c, g.ny),
+                              cz = cell_coord(ai.z, g.minz, g.inv_c, g.nz);
+                    const int cid = (cz * g.ny + cy) * g.nx + cx;
+                    if (cid != cc.cell) fill_cache(g, s_cell, cx, cy, cz, cid, cc);
+                    k = cc.total >= 0 ? gather_cached(p, atoms, s_cls, pos, ai, cc, w_cand)
+                                      : gather_candidates(p, g, atoms, s_cell, s_cls, pos, ai, w_cand);
+                }
+                if (k >= 0) {
+                    const float r = __fadd_rn(ai.w, p.probe);
+                    const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
+                    cnt = atom_fast(p, w_ent, k, nfront, w_cand, pre, s_pts);
+                    pairs += (unsigned)k;
+                } else {
+                    cnt = stats ? atom_streaming<SmemAtoms, uint16_t, true>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat)
+                                : atom_streaming<SmemAtoms, uint16_t, false>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat);
+                    streamed += 1;
+                }
+                if (lane == 0) s_val[s_orig[pos]] = cnt;
+                __syncwarp();
             }
-            if (lane == 0) s_val[s_orig[pos]] = cnt;
-            __syncwarp();
         }
         if (lane == 0 && p.stat) {
             if (pairs) atomicAdd(p.stat + 1, pairs);
