@@ -127,8 +127,10 @@ struct Proto {
 };
 #define SASA_PROTO(NT, MINB, CMAX) \
     Proto { NT, MINB, CMAX, { sasa_small_kernel<NT, MINB, false>, sasa_small_kernel<NT, MINB, true> } }
-// every configuration keeps 32 warps resident per SM (64 registers/thread)
-const Proto kProtos[] = {SASA_PROTO(256, 4, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384)};
+// 0-2 keep 32 warps resident per SM (64 registers/thread); 3-4 keep 24 warps (85 registers/thread)
+const Proto kProtos[] = {SASA_PROTO(256, 4, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384),
+                         SASA_PROTO(384, 2, 8192), SASA_PROTO(768, 1, 16384)};
+const char *kDefaultCfgs = "012";
 constexpr int kNumProtos = sizeof(kProtos) / sizeof(kProtos[0]);
 
 size_t cfg_budget(const sasa_b200_ctx *ctx, int minb) {
@@ -136,10 +138,11 @@ size_t cfg_budget(const sasa_b200_ctx *ctx, int minb) {
 }
 
 int build_cfgs(sasa_b200_ctx *ctx) {
-    const char *only = getenv("SASA_B200_CFGS");   // e.g. "0,2,3": restrict the configurations (tuning aid)
+    const char *only = getenv("SASA_B200_CFGS");   // e.g. "34": choose the configurations (tuning aid)
+    if (!only || !*only) only = kDefaultCfgs;
     for (int i = 0; i < kNumProtos; ++i) {
         const Proto &pr = kProtos[i];
-        if (only && !strchr(only, '0' + i) && i != kNumProtos - 1) continue;
+        if (!strchr(only, '0' + i)) continue;
         const size_t budget = cfg_budget(ctx, pr.minb);
         SmallCfg c{pr.nt, pr.minb, 0, pr.cmax, {0, 0}, i};
         uint32_t lo = 0, hi = 65520 / 16;   // largest nmax (multiple of 16) whose class-less layout fits
@@ -159,6 +162,8 @@ int build_cfgs(sasa_b200_ctx *ctx) {
         }
         ctx->cfgs.push_back(c);
     }
+    if (ctx->cfgs.empty()) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "SASA_B200_CFGS selects no kernel configuration");
+    std::sort(ctx->cfgs.begin(), ctx->cfgs.end(), [](const SmallCfg &a, const SmallCfg &b) { return a.nmax < b.nmax; });
     return SASA_B200_OK;
 }
 
@@ -313,7 +318,8 @@ int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
     static const int m_max = [] { const char *e = getenv("SASA_B200_M_MAX"); return e ? atoi(e) : 16; }();
     kp->m_min = m_min;
     kp->m_max = m_max;
-    kp->flags = ra.prm.flags;
+    static const uint32_t nocache = getenv("SASA_B200_NOCACHE") ? 4u : 0u;   // tuning aid
+    kp->flags = ra.prm.flags | nocache;
     kp->err_flag = ctx->d_err;
     kp->stat = ctx->d_stat;
     return SASA_B200_OK;

@@ -358,8 +358,16 @@ struct PointChunk {
     float sx[4], sy[4], sz[4];
 };
 
-__device__ __forceinline__ void load_chunk(const KParams &p, uint32_t p0, PointChunk &c) {
+__device__ __forceinline__ void load_chunk(const KParams &p, const float4 *s_pts, uint32_t p0, PointChunk &c) {
     const int lane = lane_id();
+    if (s_pts) {   // whole point set (<= 128 points) staged as float4 in shared memory
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const float4 q = s_pts[32 * s + lane];
+            c.sx[s] = q.x; c.sy[s] = q.y; c.sz[s] = q.z;
+        }
+        return;
+    }
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         const uint32_t pi = p0 + 32u * s + lane;
@@ -443,18 +451,16 @@ __device__ __forceinline__ int phase2_bcast(const KParams &p, const float4 *s_pt
 
 // Fast evaluation of one atom whose complete neighbour list sits in ent[0, k) with nfront near entries first.
 // `queue` is per-warp scratch for point indices (kQueueCap u16, may alias the candidate list).
-// `pre` holds the points of chunk 0 when n_points <= 128 (loaded once per warp, not once per atom).
 // Body points (index < n_body) go through phase 1 (first m entries, all points) and phase 2 (survivors, the
 // remaining entries); the few tail points skip phase 1 and are tested against all entries by the tile routine.
 __device__ __forceinline__ float atom_fast(const KParams &p, const float4 *ent, int k, int nfront, uint16_t *queue,
-                                           const PointChunk &pre, const float4 *s_pts) {
+                                           const float4 *s_pts) {
     const int lane = lane_id();
     int exposed = 0;
     const int m = min(k, min(max(nfront, p.m_min), p.m_max));
-    const bool single = p.n_points <= 128;
     for (uint32_t p0 = 0; p0 < p.n_points; p0 += 128) {
-        PointChunk c = pre;
-        if (!single) load_chunk(p, p0, c);
+        PointChunk c;
+        load_chunk(p, s_pts, p0, c);
         const uint32_t pend = min(p0 + 128u, p.n_points);
         const uint32_t bend = min(pend, max(p.n_body, p0));      // body points of the chunk: [p0, bend)
         const int nsl = (int)((bend - p0 + 31u) >> 5);           // slots holding at least one body point

@@ -232,10 +232,8 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
     float4 *w_ent = s_ent + warp * kNbCap;
     uint32_t *w_cand = s_cand + warp * kNbCap;
     const GlobalAtoms atoms{sorted};
-    const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0;
+    const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0, use_cache = (p.flags & 4u) == 0;
     unsigned long long pairs = 0, streamed = 0;
-    PointChunk pre;
-    load_chunk(p, 0, pre);
     const float4 *s_pts = p.n_points <= 128 ? s_ptab : nullptr;
     if (threadIdx.x < 128) {
         const bool v = threadIdx.x < p.n_points;
@@ -261,14 +259,14 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
                 const int cx = cell_coord(ai.x, g.minx, g.inv_c, g.nx), cy = cell_coord(ai.y, g.miny, g.inv_c, g.ny),
                           cz = cell_coord(ai.z, g.minz, g.inv_c, g.nz);
                 const int cid = (cz * g.ny + cy) * g.nx + cx;
-                if (cid != cc.cell) fill_cache(g, cells, cx, cy, cz, cid, cc);
+                if (use_cache && cid != cc.cell) fill_cache(g, cells, cx, cy, cz, cid, cc);
                 k = cc.total >= 0 ? gather_cached(p, atoms, cls_sorted, pos, ai, cc, w_cand)
                                   : gather_candidates(p, g, atoms, cells, cls_sorted, pos, ai, w_cand);
             }
             if (k >= 0) {
                 const float r = __fadd_rn(ai.w, p.probe);
                 const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
-                cnt = atom_fast(p, w_ent, k, nfront, reinterpret_cast<uint16_t *>(w_cand), pre, s_pts);
+                cnt = atom_fast(p, w_ent, k, nfront, reinterpret_cast<uint16_t *>(w_cand), s_pts);
                 pairs += (unsigned)k;
             } else {
                 cnt = stats ? atom_streaming<GlobalAtoms, uint32_t, true>(p, g, atoms, cells, cls_sorted, pos, w_ent, p.stat)

@@ -79,9 +79,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float4 *w_ent = s_ent + warp * kNbCap;
     uint16_t *w_cand = s_cand + warp * kQueueCap;
-    const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0;
-    PointChunk pre;
-    load_chunk(p, 0, pre);
+    const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0, use_cache = (p.flags & 4u) == 0;
     // the whole point set as a float4 table when it fits (n_points <= 128): phase 2 fetches survivors from it
     const float4 *s_pts = p.n_points <= 128 ? s_ptab : nullptr;
     if (tid < 128) {
@@ -220,14 +218,14 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
                     const int cx = cell_coord(ai.x, g.minx, g.inv_c, g.nx), cy = cell_coord(ai.y, g.miny, g.inv_c, g.ny),
                               cz = cell_coord(ai.z, g.minz, g.inv_c, g.nz);
                     const int cid = (cz * g.ny + cy) * g.nx + cx;
-                    if (cid != cc.cell) fill_cache(g, s_cell, cx, cy, cz, cid, cc);
+                    if (use_cache && cid != cc.cell) fill_cache(g, s_cell, cx, cy, cz, cid, cc);
                     k = cc.total >= 0 ? gather_cached(p, atoms, s_cls, pos, ai, cc, w_cand)
                                       : gather_candidates(p, g, atoms, s_cell, s_cls, pos, ai, w_cand);
                 }
                 if (k >= 0) {
                     const float r = __fadd_rn(ai.w, p.probe);
                     const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
-                    cnt = atom_fast(p, w_ent, k, nfront, w_cand, pre, s_pts);
+                    cnt = atom_fast(p, w_ent, k, nfront, w_cand, s_pts);
                     pairs += (unsigned)k;
                 } else {
                     cnt = stats ? atom_streaming<SmemAtoms, uint16_t, true>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat)
