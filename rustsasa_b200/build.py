@@ -22,11 +22,12 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """defines / out: build a tuning variant (e.g. defines=("-DSASA_FETCH=1",), out=".../libsasa_b200_f1.so")."""
+    if not force and out == OUT and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
@@ -35,7 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(r.stdout)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -130,7 +130,7 @@ struct Proto {
 // 0-2 keep 32 warps resident per SM (64 registers/thread); 3-4 keep 24 warps (85 registers/thread)
 const Proto kProtos[] = {SASA_PROTO(256, 4, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384),
                          SASA_PROTO(384, 2, 8192), SASA_PROTO(768, 1, 16384)};
-const char *kDefaultCfgs = "012";
+const char *kDefaultCfgs = "12";
 constexpr int kNumProtos = sizeof(kProtos) / sizeof(kProtos[0]);
 
 size_t cfg_budget(const sasa_b200_ctx *ctx, int minb) {

@@ -266,6 +266,12 @@ __device__ __forceinline__ int gather_candidates(const KParams &p, const Grid &g
 
 // Register cache of the flattened candidate list of one cell: window w of lane l is candidate 32*w + l.
 // All atoms of a cell share it, so consecutive atoms of the same cell skip rows_of / row_lookup altogether.
+#ifndef SASA_FETCH
+#define SASA_FETCH 4
+#endif
+#ifndef SASA_PRELOAD
+#define SASA_PRELOAD 0
+#endif
 constexpr int kCacheWin = 12;   // 384 candidates; denser neighbourhoods use the uncached gather
 template <typename IdxT>
 struct CandCache {
@@ -454,13 +460,14 @@ __device__ __forceinline__ int phase2_bcast(const KParams &p, const float4 *s_pt
 // Body points (index < n_body) go through phase 1 (first m entries, all points) and phase 2 (survivors, the
 // remaining entries); the few tail points skip phase 1 and are tested against all entries by the tile routine.
 __device__ __forceinline__ float atom_fast(const KParams &p, const float4 *ent, int k, int nfront, uint16_t *queue,
-                                           const float4 *s_pts) {
+                                           const float4 *s_pts, const PointChunk *pre = nullptr) {
     const int lane = lane_id();
     int exposed = 0;
     const int m = min(k, min(max(nfront, p.m_min), p.m_max));
     for (uint32_t p0 = 0; p0 < p.n_points; p0 += 128) {
         PointChunk c;
-        load_chunk(p, s_pts, p0, c);
+        if (pre) c = *pre;
+        else load_chunk(p, s_pts, p0, c);
         const uint32_t pend = min(p0 + 128u, p.n_points);
         const uint32_t bend = min(pend, max(p.n_body, p0));      // body points of the chunk: [p0, bend)
         const int nsl = (int)((bend - p0 + 31u) >> 5);           // slots holding at least one body point

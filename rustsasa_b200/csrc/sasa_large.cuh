@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
                                           v ? __ldg(p.pz + threadIdx.x) : 0.f, 0.f);
     }
     __syncthreads();
-    constexpr unsigned kFetch = 4;
+    constexpr unsigned kFetch = SASA_FETCH;
     CandCache<uint32_t> cc;
     for (;;) {
         unsigned base_u = 0;

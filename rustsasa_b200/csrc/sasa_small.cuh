@@ -200,8 +200,15 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
         // ---- per-atom work: warps pull atoms (in cell order) from a shared counter ---------------
         const SmemAtoms atoms{s_atom};
         unsigned long long pairs = 0, streamed = 0;
-        constexpr int kFetch = 4;   // consecutive cell-sorted atoms per fetch: neighbours in the list share cells
+        constexpr int kFetch = SASA_FETCH;   // consecutive cell-sorted atoms per fetch: neighbours in the list share cells
         CandCache<uint16_t> cc;
+#if SASA_PRELOAD
+        PointChunk pre;
+        load_chunk(p, s_pts, 0, pre);
+        const PointChunk *prep = p.n_points <= 128 ? &pre : nullptr;
+#else
+        const PointChunk *prep = nullptr;
+#endif
         for (;;) {
             int base = 0;
             if (lane == 0) base = atomicAdd(&s_misc[1], kFetch);
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
                 if (k >= 0) {
                     const float r = __fadd_rn(ai.w, p.probe);
                     const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
-                    cnt = atom_fast(p, w_ent, k, nfront, w_cand, s_pts);
+                    cnt = atom_fast(p, w_ent, k, nfront, w_cand, s_pts, prep);
                     pairs += (unsigned)k;
                 } else {
                     cnt = stats ? atom_streaming<SmemAtoms, uint16_t, true>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat)
