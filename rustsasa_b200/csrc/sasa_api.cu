@@ -123,10 +123,11 @@ typedef void (*SmallKernel)(const KParams);
 struct Proto {
     int nt, minb;
     uint32_t cmax;
-    SmallKernel fn[2];   // without / with id classes
+    SmallKernel fn[4];   // index = has_cls + 2 * fast (fast: n_points <= 128)
 };
-#define SASA_PROTO(NT, MINB, CMAX) \
-    Proto { NT, MINB, CMAX, { sasa_small_kernel<NT, MINB, false>, sasa_small_kernel<NT, MINB, true> } }
+#define SASA_PROTO(NT, MINB, CMAX)                                                                        \
+    Proto { NT, MINB, CMAX, { sasa_small_kernel<NT, MINB, false, false>, sasa_small_kernel<NT, MINB, true, false>, \
+                              sasa_small_kernel<NT, MINB, false, true>, sasa_small_kernel<NT, MINB, true, true> } }
 // 0-2 keep 32 warps resident per SM (64 registers/thread); 3-4 keep 24 warps (85 registers/thread)
 const Proto kProtos[] = {SASA_PROTO(256, 4, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384),
                          SASA_PROTO(384, 2, 8192), SASA_PROTO(768, 1, 16384)};
@@ -155,8 +156,8 @@ int build_cfgs(sasa_b200_ctx *ctx) {
         if (c.nmax == 0) return fail(ctx, SASA_B200_ERR_CUDA, "device shared memory too small for the fused kernel");
         c.smem[0] = small_layout(c.nmax, c.cmax, c.nt / 32, false).total;
         c.smem[1] = budget;
-        for (int v = 0; v < 2; ++v) {
-            cudaError_t e = cudaFuncSetAttribute((const void *)pr.fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem[v]);
+        for (int v = 0; v < 4; ++v) {
+            cudaError_t e = cudaFuncSetAttribute((const void *)pr.fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem[v & 1]);
             if (e != cudaSuccess)
                 return fail(ctx, SASA_B200_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", c.smem[v], cudaGetErrorString(e));
         }
@@ -358,7 +359,7 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
         const size_t smem = small_layout(kp.nmax, kp.cmax, c.nt / 32, has_cls).total;
         const int grid = (int)std::min<uint32_t>(L.n_work, (uint32_t)(ctx->sm_count * c.minb));
         void *args[] = {(void *)&kp};
-        cudaError_t e = cudaLaunchKernel((const void *)kProtos[c.proto].fn[has_cls ? 1 : 0], dim3(grid), dim3(c.nt), args, smem, st);
+        cudaError_t e = cudaLaunchKernel((const void *)kProtos[c.proto].fn[(has_cls ? 1 : 0) + (kp.n_points <= 128 ? 2 : 0)], dim3(grid), dim3(c.nt), args, smem, st);
         if (e != cudaSuccess) return fail(ctx, SASA_B200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
         ++*launches;
     }

@@ -298,7 +298,11 @@ __device__ __forceinline__ void fill_cache(const Grid &g, const CellT *cell, int
     if (cc.total < 0) return;
 #pragma unroll
     for (int w = 0; w < kCacheWin; ++w)
-        if (32 * w < rows.total) cc.set(w, row_lookup(rows, 32 * w + lane_id()));
+        if (32 * w < rows.total) {
+            const int idx = 32 * w + lane_id();
+            const int j = row_lookup(rows, idx);
+            cc.set(w, idx < rows.total ? j : 0);   // slots past the end hold a harmless in-range position
+        }
 }
 
 // Pass 1 through the cache: same result as gather_candidates.

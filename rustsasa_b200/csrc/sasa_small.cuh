@@ -9,8 +9,12 @@
 // (src/lib.rs:94-224), the driver loop (src/lib.rs:249-298) and the numeric part of process_atoms
 // (src/options.rs:195-232, :292-315, :370-410).  CTAs are persistent and pull structures from an
 // atomic queue ordered largest-first by the host.
+//
+// Template parameters: NT threads, MINB resident CTAs per SM, HAS_CLS (Atom.id equality classes present),
+// FAST (n_points <= 128: the tight pipeline of sasa_fast.cuh; otherwise the generic chunked routines).
 #pragma once
 #include "sasa_device.cuh"
+#include "sasa_fast.cuh"
 
 namespace sasa {
 
@@ -19,73 +23,88 @@ struct SmemAtoms {
     __device__ __forceinline__ float4 operator()(int j) const { return a[j]; }
 };
 
+// Shared-memory layout.  Everything the per-atom loops touch sits at compile-time offsets (given the warp
+// count), so no base pointer has to stay in a register: point table | per-warp entries | per-warp index
+// lists | reduction scratch | misc | atoms | per-atom values | [classes] | original indices | cell table.
 struct SmallLayout {
-    size_t atom, ent, pts, val, cls, cellw, red, misc, orig, cand, total;
+    size_t pts, ent, cand, red, misc, atom, val, cls, orig, cellw, total;
 };
+
+__host__ __device__ constexpr size_t small_fixed_bytes(int nwarps) {
+    return 128 * 16 + (size_t)nwarps * kNbCap * 16 + (size_t)nwarps * kQueueCap * 2 + 32 * 8 * 4 + 64;
+}
 
 __host__ __device__ inline SmallLayout small_layout(uint32_t nmax, uint32_t cmax, int nwarps, bool has_cls) {
     SmallLayout L;
     size_t o = 0;
-    L.atom = o;  o += (size_t)nmax * 16;
-    L.ent = o;   o += (size_t)nwarps * kNbCap * 16;
     L.pts = o;   o += 128 * 16;
-    L.val = o;   o += (size_t)nmax * 4;
-    L.cls = o;   o += has_cls ? (size_t)nmax * 4 : 0;
-    L.cellw = o; o += (((size_t)cmax + 2 + 1) / 2) * 4;
+    L.ent = o;   o += (size_t)nwarps * kNbCap * 16;
+    L.cand = o;  o += (size_t)nwarps * kQueueCap * 2;
     L.red = o;   o += 32 * 8 * 4;
     L.misc = o;  o += 64;
+    L.atom = o;  o += (size_t)nmax * 16;
+    L.val = o;   o += (size_t)nmax * 4;
+    L.cls = o;   o += has_cls ? (size_t)nmax * 4 : 0;
     L.orig = o;  o += (size_t)nmax * 2;
-    L.cand = o;  o += (size_t)nwarps * kQueueCap * 2;
+    o = (o + 3) & ~(size_t)3;
+    L.cellw = o; o += (((size_t)cmax + 2 + 1) / 2) * 4;
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
 
+// min or max of 8 per-thread values over the block; result valid in every thread.
 template <int NT>
-__device__ __forceinline__ float block_reduce_minmax(float v, bool is_max, float *red) {
-    // returns the reduction in every thread; red must hold NT/32 floats; caller syncs between uses
+__device__ __forceinline__ void block_minmax8(float (&v)[8], float *red) {
     const int lane = lane_id(), w = threadIdx.x >> 5;
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        const float o = __shfl_xor_sync(kFull, v, d);
-        v = is_max ? fmaxf(v, o) : fminf(v, o);
+    for (int d = 16; d >= 1; d >>= 1)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], __shfl_xor_sync(kFull, v[k], d));
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[w * 8 + k] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float r = red[k];
+        for (int i = 1; i < NT / 32; ++i) r = fmaxf(r, red[i * 8 + k]);
+        v[k] = r;
     }
-    if (lane == 0) red[w] = v;
     __syncthreads();
-    float r = red[0];
-    for (int i = 1; i < NT / 32; ++i) r = is_max ? fmaxf(r, red[i]) : fminf(r, red[i]);
-    __syncthreads();
-    return r;
 }
 
-template <int NT, int MINB, bool HAS_CLS>
+template <int NT, int MINB, bool HAS_CLS, bool FAST>
 __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NW = NT / 32;
+    constexpr size_t kOffEnt = 128 * 16, kOffCand = kOffEnt + (size_t)NW * kNbCap * 16,
+                     kOffRed = kOffCand + (size_t)NW * kQueueCap * 2, kOffMisc = kOffRed + 32 * 8 * 4,
+                     kOffAtom = kOffMisc + 64;
+    static_assert(kOffAtom == small_fixed_bytes(NW), "layout mismatch");
+    float4 *const s_ptab = reinterpret_cast<float4 *>(smem);
+    float4 *const s_atom = reinterpret_cast<float4 *>(smem + kOffAtom);
+    float *const s_red = reinterpret_cast<float *>(smem + kOffRed);
+    int *const s_misc = reinterpret_cast<int *>(smem + kOffMisc);
     const SmallLayout L = small_layout(p.nmax, p.cmax, NW, HAS_CLS);
-    float4 *s_atom = reinterpret_cast<float4 *>(smem + L.atom);
-    float4 *s_ent = reinterpret_cast<float4 *>(smem + L.ent);
-    float4 *s_ptab = reinterpret_cast<float4 *>(smem + L.pts);
     float *s_val = reinterpret_cast<float *>(smem + L.val);
     uint16_t *s_cellid = reinterpret_cast<uint16_t *>(smem + L.val);  // aliases s_val during the sort
     uint16_t *s_rank = s_cellid + p.nmax;
     uint32_t *s_cls = HAS_CLS ? reinterpret_cast<uint32_t *>(smem + L.cls) : nullptr;
+    uint16_t *s_orig = reinterpret_cast<uint16_t *>(smem + L.orig);
     uint32_t *s_cellw = reinterpret_cast<uint32_t *>(smem + L.cellw);
     uint16_t *s_cell = reinterpret_cast<uint16_t *>(smem + L.cellw);
-    float *s_red = reinterpret_cast<float *>(smem + L.red);
-    int *s_misc = reinterpret_cast<int *>(smem + L.misc);
-    uint16_t *s_orig = reinterpret_cast<uint16_t *>(smem + L.orig);
-    uint16_t *s_cand = reinterpret_cast<uint16_t *>(smem + L.cand);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float4 *w_ent = s_ent + warp * kNbCap;
-    uint16_t *w_cand = s_cand + warp * kQueueCap;
-    const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0, use_cache = (p.flags & 4u) == 0;
-    // the whole point set as a float4 table when it fits (n_points <= 128): phase 2 fetches survivors from it
+    float4 *const w_ent = reinterpret_cast<float4 *>(smem + kOffEnt) + warp * kNbCap;
+    uint16_t *const w_cand = reinterpret_cast<uint16_t *>(smem + kOffCand) + warp * kQueueCap;
+    const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0;
+    // the whole point set as a float4 table when it fits (n_points <= 128)
     const float4 *s_pts = p.n_points <= 128 ? s_ptab : nullptr;
     if (tid < 128) {
         const bool v = (uint32_t)tid < p.n_points;
         s_ptab[tid] = make_float4(v ? __ldg(p.px + tid) : 0.f, v ? __ldg(p.py + tid) : 0.f, v ? __ldg(p.pz + tid) : 0.f, 0.f);
     }
+    const int nbody = (int)min(p.n_points, p.n_body), nsl = (nbody + 31) >> 5;
 
     for (;;) {
         __syncthreads();
@@ -98,26 +117,20 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
         const int N = (int)(p.struct_off[sid + 1] - a0);
         const float4 *gat = p.xyzr + a0;
 
-        // ---- bounds, r_max, finiteness -------------------------------------------------------
-        float mnx = INFINITY, mny = INFINITY, mnz = INFINITY, mxx = -INFINITY, mxy = -INFINITY, mxz = -INFINITY,
-              rmax = 0.0f;
-        bool finite = true;
+        // ---- bounds, r_max, finiteness (one fused block reduction: maxima of {-min, max, r, bad}) -------------
+        float red8[8] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0f, 0.0f};
         for (int i = tid; i < N; i += NT) {
             const float4 a = __ldg(gat + i);
-            finite = finite && isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(a.w);
-            mnx = fminf(mnx, a.x); mny = fminf(mny, a.y); mnz = fminf(mnz, a.z);
-            mxx = fmaxf(mxx, a.x); mxy = fmaxf(mxy, a.y); mxz = fmaxf(mxz, a.z);
-            rmax = fmaxf(rmax, a.w);
+            const bool fin = isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(a.w);
+            red8[0] = fmaxf(red8[0], -a.x); red8[1] = fmaxf(red8[1], -a.y); red8[2] = fmaxf(red8[2], -a.z);
+            red8[3] = fmaxf(red8[3], a.x);  red8[4] = fmaxf(red8[4], a.y);  red8[5] = fmaxf(red8[5], a.z);
+            red8[6] = fmaxf(red8[6], a.w);
+            if (!fin) red8[7] = 1.0f;
         }
-        mnx = block_reduce_minmax<NT>(mnx, false, s_red);
-        mny = block_reduce_minmax<NT>(mny, false, s_red);
-        mnz = block_reduce_minmax<NT>(mnz, false, s_red);
-        mxx = block_reduce_minmax<NT>(mxx, true, s_red);
-        mxy = block_reduce_minmax<NT>(mxy, true, s_red);
-        mxz = block_reduce_minmax<NT>(mxz, true, s_red);
-        rmax = block_reduce_minmax<NT>(rmax, true, s_red);
-        const float bad = block_reduce_minmax<NT>(finite ? 0.0f : 1.0f, true, s_red);
-        if (bad != 0.0f) {
+        block_minmax8<NT>(red8, s_red);
+        const float mnx = -red8[0], mny = -red8[1], mnz = -red8[2], mxx = red8[3], mxy = red8[4], mxz = red8[5],
+                    rmax = red8[6];
+        if (red8[7] != 0.0f) {
             // the reference panics on non-finite input; report it and emit NaN for this structure
             if (tid == 0) atomicExch(p.err_flag, 4);
             const float qn = __int_as_float(0x7fc00000);
@@ -197,55 +210,61 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
         if (tid == 0) s_misc[1] = 0;
         __syncthreads();   // s_cellid / s_rank are dead from here on: s_val may be written
 
-        // ---- per-atom work: warps pull atoms (in cell order) from a shared counter ---------------
+        // ---- per-atom work: warps pull runs of consecutive cell-sorted atoms from a shared counter ----------
         const SmemAtoms atoms{s_atom};
-        unsigned long long pairs = 0, streamed = 0;
-        constexpr int kFetch = SASA_FETCH;   // consecutive cell-sorted atoms per fetch: neighbours in the list share cells
+        unsigned pairs = 0, streamed = 0;
+        constexpr int kFetch = SASA_FETCH;
         CandCache<uint16_t> cc;
-#if SASA_PRELOAD
-        PointChunk pre;
-        load_chunk(p, s_pts, 0, pre);
-        const PointChunk *prep = p.n_points <= 128 ? &pre : nullptr;
-#else
-        const PointChunk *prep = nullptr;
-#endif
         for (;;) {
             int base = 0;
             if (lane == 0) base = atomicAdd(&s_misc[1], kFetch);
             base = __shfl_sync(kFull, base, 0);
             if (base >= N) break;
-            cc.cell = -1;
+            int cell_end = -1;   // atoms [.., cell_end) share the cached candidate list
             cc.total = -1;
             const int pend = min(base + kFetch, N);
             for (int pos = base; pos < pend; ++pos) {
                 const float4 ai = s_atom[pos];
-                float cnt;
+                int cnt;
                 int k = -1;
                 if (!force_stream && !stats) {
-                    const int cx = cell_coord(ai.x, g.minx, g.inv_c, g.nx), cy = cell_coord(ai.y, g.miny, g.inv_c, g.ny),
-                              cz = cell_coord(ai.z, g.minz, g.inv_c, g.nz);
-                    const int cid = (cz * g.ny + cy) * g.nx + cx;
-                    if (use_cache && cid != cc.cell) fill_cache(g, s_cell, cx, cy, cz, cid, cc);
-                    k = cc.total >= 0 ? gather_cached(p, atoms, s_cls, pos, ai, cc, w_cand)
-                                      : gather_candidates(p, g, atoms, s_cell, s_cls, pos, ai, w_cand);
+                    if (pos >= cell_end) {
+                        const int cx = cell_coord(ai.x, g.minx, g.inv_c, g.nx), cy = cell_coord(ai.y, g.miny, g.inv_c, g.ny),
+                                  cz = cell_coord(ai.z, g.minz, g.inv_c, g.nz);
+                        const int cid = (cz * g.ny + cy) * g.nx + cx;
+                        cell_end = (int)s_cell[cid + 1];
+                        fill_cache(g, s_cell, cx, cy, cz, cid, cc);
+                    }
+                    if (cc.total >= 0) {
+                        if (FAST) k = fast_gather<HAS_CLS>(s_atom, s_cls, pos, ai, ai.w + 2.0f * p.probe + kCutSlack, cc, w_cand);
+                        else k = gather_cached(p, atoms, s_cls, pos, ai, cc, w_cand);
+                    } else {
+                        k = gather_candidates(p, g, atoms, s_cell, s_cls, pos, ai, w_cand);
+                    }
+                    if (k > kNbCap) k = -1;
                 }
                 if (k >= 0) {
                     const float r = __fadd_rn(ai.w, p.probe);
-                    const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
-                    cnt = atom_fast(p, w_ent, k, nfront, w_cand, s_pts, prep);
+                    if (FAST) {
+                        const int nfront = fast_entries(s_atom, ai, p.probe, __fmul_rn(r, r), __fmul_rn(2.0f, r), p.near2, w_cand, k, w_ent);
+                        cnt = fast_atom(p, w_ent, k, nfront, s_ptab, w_cand, nbody, nsl);
+                    } else {
+                        const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
+                        cnt = (int)atom_fast(p, w_ent, k, nfront, w_cand, s_pts);
+                    }
                     pairs += (unsigned)k;
                 } else {
-                    cnt = stats ? atom_streaming<SmemAtoms, uint16_t, true>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat)
-                                : atom_streaming<SmemAtoms, uint16_t, false>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat);
+                    cnt = (int)(stats ? atom_streaming<SmemAtoms, uint16_t, true>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat)
+                                      : atom_streaming<SmemAtoms, uint16_t, false>(p, g, atoms, s_cell, s_cls, pos, w_ent, p.stat));
                     streamed += 1;
                 }
-                if (lane == 0) s_val[s_orig[pos]] = cnt;
+                if (lane == 0) s_val[s_orig[pos]] = (float)cnt;
                 __syncwarp();
             }
         }
         if (lane == 0 && p.stat) {
-            if (pairs) atomicAdd(p.stat + 1, pairs);
-            if (streamed) atomicAdd(p.stat + 2, streamed);
+            if (pairs) atomicAdd(p.stat + 1, (unsigned long long)pairs);
+            if (streamed) atomicAdd(p.stat + 2, (unsigned long long)streamed);
         }
         __syncthreads();
 
