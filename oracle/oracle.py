@@ -10,17 +10,37 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _build(target: str) -> None:
-    subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL)
+def _build(target: str, *extra: str) -> None:
+    subprocess.run(["make", "-C", _HERE, target, *extra], check=True, stdout=subprocess.DEVNULL)
+
+
+def _cpu_tag() -> str:
+    """Short hash of this host's CPU model + ISA flags: the -march=native build is only valid on the CPU it was
+    built on, and built .so files travel from the build container to the GPU box."""
+    import hashlib
+    sig = ""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith(("model name", "flags")):
+                    sig += line
+                if line.startswith("flags"):
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1(sig.encode()).hexdigest()[:10]
 
 
 class Oracle:
     def __init__(self, fast: bool = False):
-        name = "liboracle_fast.so" if fast else "liboracle.so"
+        name = f"liboracle_fast_{_cpu_tag()}.so" if fast else "liboracle.so"
         path = os.path.join(_HERE, name)
         src = os.path.join(_HERE, "sasa_oracle.c")
         if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
-            _build("fast" if fast else "all")
+            if fast:
+                _build("fast", f"FAST_OUT={name}")
+            else:
+                _build("all")
         self.lib = L = C.CDLL(path)
         fp, u32p, u64p, u8p = (C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                C.POINTER(C.c_uint8))
