@@ -26,6 +26,7 @@
 
 #include "sasa_large.cuh"
 #include "sasa_small.cuh"
+#include "sasa_tight.cuh"
 
 using namespace sasa;
 
@@ -123,11 +124,11 @@ typedef void (*SmallKernel)(const KParams);
 struct Proto {
     int nt, minb;
     uint32_t cmax;
-    SmallKernel fn[4];   // index = has_cls + 2 * fast (fast: n_points <= 128)
+    SmallKernel fn[4];   // index = has_cls + 2 * tight (tight: n_points <= 128, no statistics / forced streaming)
 };
 #define SASA_PROTO(NT, MINB, CMAX)                                                                        \
-    Proto { NT, MINB, CMAX, { sasa_small_kernel<NT, MINB, false, false>, sasa_small_kernel<NT, MINB, true, false>, \
-                              sasa_small_kernel<NT, MINB, false, true>, sasa_small_kernel<NT, MINB, true, true> } }
+    Proto { NT, MINB, CMAX, { sasa_small_kernel<NT, MINB, false>, sasa_small_kernel<NT, MINB, true>, \
+                              sasa_tight_kernel<NT, MINB, false>, sasa_tight_kernel<NT, MINB, true> } }
 // 0-2 keep 32 warps resident per SM (64 registers/thread); 3-4 keep 24 warps (85 registers/thread)
 const Proto kProtos[] = {SASA_PROTO(256, 4, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384),
                          SASA_PROTO(384, 2, 8192), SASA_PROTO(768, 1, 16384)};
@@ -359,7 +360,7 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
         const size_t smem = small_layout(kp.nmax, kp.cmax, c.nt / 32, has_cls).total;
         const int grid = (int)std::min<uint32_t>(L.n_work, (uint32_t)(ctx->sm_count * c.minb));
         void *args[] = {(void *)&kp};
-        cudaError_t e = cudaLaunchKernel((const void *)kProtos[c.proto].fn[(has_cls ? 1 : 0) + (kp.n_points <= 128 ? 2 : 0)], dim3(grid), dim3(c.nt), args, smem, st);
+        cudaError_t e = cudaLaunchKernel((const void *)kProtos[c.proto].fn[(has_cls ? 1 : 0) + ((kp.n_points <= 128 && (kp.flags & 3u) == 0) ? 2 : 0)], dim3(grid), dim3(c.nt), args, smem, st);
         if (e != cudaSuccess) return fail(ctx, SASA_B200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
         ++*launches;
     }

@@ -1,0 +1,309 @@
+// sasa_tight.cuh -- the fused per-structure kernel for n_points <= 128 (the reference's default, 100 points,
+// is the headline configuration).  Same stages as the generic kernel of sasa_small.cuh, but the per-atom
+// pipeline is written for a SMALL INSTRUCTION FOOTPRINT: the generic kernel's hot code spans ~45 KB of SASS,
+// more than the SM's 32 KB L1.5 instruction cache, and ncu showed 37 % of its stall cycles as "no instruction"
+// (profiles/r01a_baseline.txt).  Here every stage is one short rolled loop, the cell's candidate list lives in
+// shared memory instead of unrolled register windows, the tile routine takes its shape at run time, and the
+// never-taken fallbacks (dense clusters) sit behind one __noinline__ call.
+//
+// Per cell (one warp owns a run of consecutive cells):
+//   list     the (2e+1)^2 cell rows around the cell are contiguous ranges of the cell-sorted atom array; their
+//            positions are flattened once into a per-warp u16 list, padded to a multiple of 32 with the
+//            far-away sentinel atom
+// Per atom of the cell:
+//   gather   32 listed candidates per step: distance test, ballot, compaction into a u16 neighbour list
+//   entries  (vx, vy, vz, limit) per neighbour with the reference's arithmetic, "near" neighbours first
+//   phase 1  all body points (3 slots per lane for n = 100) against the first m entries:
+//            one broadcast LDS.128 + 3 x (FMUL, 2 FFMA, FSETP.LT.OR) per entry
+//   phase 2  the surviving points against the remaining entries as a G x (32/G) tile of (survivor, entry) pairs
+//   tail     the n mod lanes tail points (unfused dot, <=) against all entries, same tile form
+#pragma once
+#include "sasa_small.cuh"
+
+namespace sasa {
+
+#ifndef SASA_CELL_FETCH
+#define SASA_CELL_FETCH 4
+#endif
+
+// Flatten the candidate rows of cell (cx, cy, cz) into list[0, total) (positions in the sorted atom array),
+// padded with `sentinel` up to the next multiple of 32.  Returns total, or -1 when it exceeds kListCap.
+__device__ __forceinline__ int tight_fill_list(const Grid &g, const uint16_t *cell, int cx, int cy, int cz,
+                                               uint16_t *list, int sentinel) {
+    const int lane = lane_id();
+    const int w = 2 * g.e + 1;
+    const int dy = lane % w - g.e, dz = lane / w - g.e;
+    const int y = cy + dy, z = cz + dz;
+    int start = 0, len = 0;
+    if (lane < w * w && y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+        const int x0 = max(cx - g.e, 0), x1 = min(cx + g.e, g.nx - 1);
+        const int base = (z * g.ny + y) * g.nx;
+        start = (int)cell[base + x0];
+        len = (int)cell[base + x1 + 1] - start;
+    }
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(kFull, incl, 31);
+    if (total > kListCap) return -1;
+    const int maxlen = __reduce_max_sync(kFull, len);
+    uint16_t *dst = list + (incl - len);
+#pragma unroll 1
+    for (int t = 0; t < maxlen; ++t)
+        if (t < len) dst[t] = (uint16_t)(start + t);
+    const int pad = total + lane;
+    if (pad < ((total + 31) & ~31)) list[pad] = (uint16_t)sentinel;
+    __syncwarp();
+    return total;
+}
+
+// Neighbours of atom `pos` among the listed candidates: positions of all atoms within r_i + r_j + 2*probe
+// (+ slack) go to cand[0, k).  Membership is result-neutral (any superset of the overlapping pairs gives the
+// same counts), so this test may use contracted arithmetic; the 1e-3 A slack absorbs its rounding.
+template <bool HAS_CLS>
+__device__ __forceinline__ int tight_gather(const float4 *s_atom, const uint32_t *s_cls, const uint16_t *list, int total,
+                                            int pos, const float4 ai, float reach_i, uint16_t *cand) {
+    const int lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const uint32_t cls_i = HAS_CLS ? s_cls[pos] : 0u;
+    int k = 0;
+#pragma unroll 2
+    for (int w0 = 0; w0 < total; w0 += 32) {
+        const int j = (int)list[w0 + lane];
+        const float4 aj = s_atom[j];
+        const float dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
+        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        const float cut = reach_i + aj.w;
+        bool acc = (d2 <= cut * cut) & (j != pos);          // sentinel pads fail the distance test
+        if (HAS_CLS) acc = acc && (s_cls[j] != cls_i);       // (the sentinel slot of s_cls is never read: && short-circuits)
+        const unsigned m = __ballot_sync(kFull, acc);
+        const int at = k + __popc(m & lt);
+        if (acc & (at < kQueueCap)) cand[at] = (uint16_t)j;
+        k += __popc(m);
+    }
+    __syncwarp();
+    return k;
+}
+
+// (vx, vy, vz, limit) per neighbour -- the per-pair setup of src/lib.rs:128-136 -- with the "near" neighbours
+// (centre distance^2 < near2) packed at the front and the rest at the back.  Returns the number of near entries.
+__device__ __forceinline__ int tight_entries(const float4 *s_atom, const float4 ai, float probe, float r2, float two_r,
+                                             float near2, const uint16_t *cand, int k, float4 *ent) {
+    const int lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    int nfront = 0, nback = k - 1;
+#pragma unroll 1
+    for (int q0 = 0; q0 < k; q0 += 32) {
+        const int q = q0 + lane;
+        const bool valid = q < k;
+        const float4 aj = s_atom[valid ? (int)cand[q] : 0];
+        float vmag;
+        const float4 e = make_entry(ai, aj, probe, r2, two_r, &vmag);
+        const bool near = valid & (vmag < near2);
+        const unsigned mn = __ballot_sync(kFull, near);
+        const unsigned mv = __ballot_sync(kFull, valid);
+        const unsigned mf = mv & ~mn;
+        const int at = near ? nfront + __popc(mn & lt) : nback - __popc(mf & lt);
+        if (valid) ent[at] = e;
+        nfront += __popc(mn);
+        nback -= __popc(mf);
+    }
+    __syncwarp();
+    return nfront;
+}
+
+// Phase 1: NSL slots of body points per lane against entries [0, m).  Returns the per-slot "still exposed" ballots.
+template <int NSL>
+__device__ __forceinline__ void tight_phase1(const float4 *ent, int m, const float4 *pts, int nbody, unsigned (&live)[4]) {
+    const int lane = lane_id();
+    float4 p0 = pts[lane], p1, p2, p3;
+    if (NSL > 1) p1 = pts[32 + lane];
+    if (NSL > 2) p2 = pts[64 + lane];
+    if (NSL > 3) p3 = pts[96 + lane];
+    // scalar flags so that ptxas keeps them in predicate registers: FSETP.LT.OR P, dot, limit, P
+    bool o0 = lane >= nbody, o1 = 32 + lane >= nbody, o2 = 64 + lane >= nbody, o3 = 96 + lane >= nbody;
+#pragma unroll 2
+    for (int q = 0; q < m; ++q) {
+        const float4 e = ent[q];
+        o0 = o0 || (dot_body(p0.x, p0.y, p0.z, e) < e.w);
+        if (NSL > 1) o1 = o1 || (dot_body(p1.x, p1.y, p1.z, e) < e.w);
+        if (NSL > 2) o2 = o2 || (dot_body(p2.x, p2.y, p2.z, e) < e.w);
+        if (NSL > 3) o3 = o3 || (dot_body(p3.x, p3.y, p3.z, e) < e.w);
+    }
+    live[0] = __ballot_sync(kFull, !o0);
+    live[1] = NSL > 1 ? __ballot_sync(kFull, !o1) : 0u;
+    live[2] = NSL > 2 ? __ballot_sync(kFull, !o2) : 0u;
+    live[3] = NSL > 3 ? __ballot_sync(kFull, !o3) : 0u;
+}
+
+// ns (1..32) points listed in queue[0, ns) against entries [q0, k) as a (point x entry) tile: with G the power
+// of two >= ns, lane l owns point (l mod G) and entry offset (l div G), so one step tests 32/G entries against
+// every point.  Returns how many points no entry occludes.
+template <bool TAIL>
+__device__ __forceinline__ int tight_tile(const float4 *ent, int q0, int k, const float4 *pts, const uint16_t *queue, int ns) {
+    const int lane = lane_id();
+    const int sh = 32 - __clz(ns - 1);            // ns = 1 -> clz(0) = 32 -> sh = 0
+    const int G = 1 << sh;
+    const int sidx = lane & (G - 1);
+    const float4 pt = pts[sidx < ns ? (int)queue[sidx] : 0];
+    const int kstep = 32 >> sh;
+    bool hit = false;
+#pragma unroll 1
+    for (int q = q0 + (lane >> sh); q < k; q += kstep) {
+        const float4 e = ent[q];
+        if (TAIL) hit = hit | (dot_tail(pt.x, pt.y, pt.z, e) <= e.w);
+        else hit = hit | (dot_body(pt.x, pt.y, pt.z, e) < e.w);
+    }
+    unsigned mk = __ballot_sync(kFull, hit);
+#pragma unroll 1
+    for (int st = 16; st >= G; st >>= 1) mk |= mk >> st;    // OR over the lanes that share a point
+    const unsigned valid = ns >= 32 ? 0xffffffffu : ((1u << ns) - 1u);
+    return __popc(~mk & valid);
+}
+
+// One atom with its complete neighbour list in ent[0, k), nfront near entries first.  nbody = body points
+// (index < n_body), the tail points are [nbody, n_points).  Returns the exposed-point count.
+template <int NSL>
+__device__ __forceinline__ int tight_atom(const KParams &p, const float4 *ent, int k, int nfront, const float4 *pts,
+                                          uint16_t *queue, int nbody) {
+    const int lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const int m = min(k, min(max(nfront, p.m_min), p.m_max));
+    unsigned live[4];
+    tight_phase1<NSL>(ent, m, pts, nbody, live);
+    int exposed = 0;
+    const int ns = __popc(live[0]) + __popc(live[1]) + __popc(live[2]) + __popc(live[3]);
+    if (m == k) {
+        exposed = ns;
+    } else if (ns) {
+        int at = 0;     // survivors -> queue, slot-major
+#pragma unroll
+        for (int s = 0; s < NSL; ++s) {
+            if ((live[s] >> lane) & 1u) queue[at + __popc(live[s] & lt)] = (uint16_t)(32 * s + lane);
+            at += __popc(live[s]);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int b = 0; b < ns; b += 32) exposed += tight_tile<false>(ent, m, k, pts, queue + b, min(32, ns - b));
+        __syncwarp();
+    }
+    const int ntail = (int)p.n_points - nbody;
+    if (ntail) {
+        if (k == 0) {
+            exposed += ntail;
+        } else {
+#pragma unroll 1
+            for (int t0 = 0; t0 < ntail; t0 += 32) {
+                const int nt = min(32, ntail - t0);
+                if (lane < nt) queue[lane] = (uint16_t)(nbody + t0 + lane);
+                __syncwarp();
+                exposed += tight_tile<true>(ent, 0, k, pts, queue, nt);
+                __syncwarp();
+            }
+        }
+    }
+    return exposed;
+}
+
+// Cold path, out of line on purpose.  Cells with more than kListCap candidates (structures whose bounding box
+// forced a coarser grid) take the generic per-atom gather and the generic chunked evaluation; atoms with more
+// than kNbCap neighbours (denser than any protein) the list-free streaming routine.  Returns the exposed-point
+// count and adds the atom's list length to *pairs, or 1 to *streamed.
+template <bool HAS_CLS>
+__device__ __noinline__ int tight_cold_atom(const float *px, const float *py, const float *pz, uint32_t n_points, uint32_t n_body,
+                                            float probe, float near2, int m_min, int m_max, Grid g, const float4 *s_atom,
+                                            const uint16_t *s_cell, const uint32_t *s_cls, const float4 *s_pts, int pos,
+                                            float4 *ent, uint16_t *cand, unsigned *pairs, unsigned *streamed) {
+    KParams q;
+    q.px = px; q.py = py; q.pz = pz;
+    q.n_points = n_points; q.n_body = n_body; q.probe = probe;
+    q.near2 = near2; q.m_min = m_min; q.m_max = m_max; q.bcast_min = 16;
+    const SmemAtoms atoms{s_atom};
+    const uint32_t *cls = HAS_CLS ? s_cls : nullptr;
+    const float4 ai = s_atom[pos];
+    const int k = gather_candidates(q, g, atoms, s_cell, cls, pos, ai, cand);
+    if (k >= 0) {
+        const float r = __fadd_rn(ai.w, probe);
+        const int nfront = build_entries(q, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), cand, k, ent);
+        *pairs += (unsigned)k;
+        return (int)atom_fast(q, ent, k, nfront, cand, s_pts);
+    }
+    *streamed += 1;
+    return (int)atom_streaming<SmemAtoms, uint16_t, false>(q, g, atoms, s_cell, cls, pos, ent, nullptr);
+}
+
+template <int NT, int MINB, bool HAS_CLS>
+__global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NW = NT / 32;
+    constexpr size_t kOffEnt = 128 * 16, kOffCand = kOffEnt + (size_t)NW * kNbCap * 16,
+                     kOffList = kOffCand + (size_t)NW * kQueueCap * 2;
+    const SmemView V = smem_view<NT, HAS_CLS>(smem, p);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 *const w_ent = reinterpret_cast<float4 *>(smem + kOffEnt) + warp * kNbCap;
+    uint16_t *const w_cand = reinterpret_cast<uint16_t *>(smem + kOffCand) + warp * kQueueCap;
+    uint16_t *const w_list = reinterpret_cast<uint16_t *>(smem + kOffList) + warp * kListCap;
+    stage_points(p, V.ptab);
+    const int nbody = (int)min(p.n_points, p.n_body), nsl = (nbody + 31) >> 5;
+    const float reach0 = 2.0f * p.probe + kCutSlack;
+
+    uint32_t sid, a0;
+    int N;
+    while (claim_structure(p, V.misc, sid, a0, N)) {
+        Grid g;
+        int ncell;
+        if (!structure_setup<NT, HAS_CLS>(p, V, sid, a0, N, g, ncell)) continue;
+
+        // ---- per-atom work: warps claim runs of consecutive cells; the atoms of a cell share its candidate list ----
+        unsigned pairs = 0, streamed = 0;
+        for (;;) {
+            int c0 = 0;
+            if (lane == 0) c0 = atomicAdd(&V.misc[1], SASA_CELL_FETCH);
+            c0 = __shfl_sync(kFull, c0, 0);
+            if (c0 >= ncell) break;
+            const int c1 = min(c0 + SASA_CELL_FETCH, ncell);
+            int pos = (int)V.cell[c0];
+            const int pos_end = (int)V.cell[c1];
+            while (pos < pos_end) {
+                // the cell of atom `pos` and the end of its run in the sorted array
+                const float4 a_first = V.atom[pos];
+                const int cx = cell_coord(a_first.x, g.minx, g.inv_c, g.nx), cy = cell_coord(a_first.y, g.miny, g.inv_c, g.ny),
+                          cz = cell_coord(a_first.z, g.minz, g.inv_c, g.nz);
+                const int cell_end = (int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1];
+                const int total = tight_fill_list(g, V.cell, cx, cy, cz, w_list, N);
+                for (; pos < cell_end; ++pos) {
+                    const float4 ai = V.atom[pos];
+                    int cnt;
+                    int k = total >= 0 ? tight_gather<HAS_CLS>(V.atom, V.cls, w_list, total, pos, ai, ai.w + reach0, w_cand)
+                                       : kNbCap + 1;
+                    if (k <= kNbCap) {
+                        const float r = __fadd_rn(ai.w, p.probe);
+                        const int nfront = tight_entries(V.atom, ai, p.probe, __fmul_rn(r, r), __fmul_rn(2.0f, r), p.near2,
+                                                         w_cand, k, w_ent);
+                        if (nsl == 3) cnt = tight_atom<3>(p, w_ent, k, nfront, V.ptab, w_cand, nbody);
+                        else if (nsl == 4) cnt = tight_atom<4>(p, w_ent, k, nfront, V.ptab, w_cand, nbody);
+                        else if (nsl == 2) cnt = tight_atom<2>(p, w_ent, k, nfront, V.ptab, w_cand, nbody);
+                        else cnt = tight_atom<1>(p, w_ent, k, nfront, V.ptab, w_cand, nbody);
+                        pairs += (unsigned)k;
+                    } else {
+                        cnt = tight_cold_atom<HAS_CLS>(p.px, p.py, p.pz, p.n_points, p.n_body, p.probe, p.near2, p.m_min, p.m_max,
+                                                       g, V.atom, V.cell, V.cls, V.ptab, pos, w_ent, w_cand, &pairs, &streamed);
+                    }
+                    if (lane == 0) V.val[V.orig[pos]] = (float)cnt;
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane == 0 && p.stat) {
+            if (pairs) atomicAdd(p.stat + 1, (unsigned long long)pairs);
+            if (streamed) atomicAdd(p.stat + 2, (unsigned long long)streamed);
+        }
+        __syncthreads();
+        structure_outputs<NT>(p, V, sid, a0, N);
+    }
+}
+
+}  // namespace sasa
