@@ -139,36 +139,42 @@ __device__ __forceinline__ void tight_phase1(const float4 *ent, int m, const flo
     live[3] = NSL > 3 ? __ballot_sync(kFull, !o3) : 0u;
 }
 
-// ns (1..32) points listed in queue[0, ns) against entries [q0, k) as a (point x entry) tile: with G the power
-// of two >= ns, lane l owns point (l mod G) and entry offset (l div G), so one step tests 32/G entries against
-// every point.  Returns how many points no entry occludes.
+// Shape of a (point x entry) tile for ns (1..32) points: G = 2^sh is the power of two >= ns; lane l owns point
+// (l mod G) and entry offset (l div G), so one step tests 32/G entries against every point.
+__device__ __forceinline__ int tile_shift(int ns) { return 32 - __clz(ns - 1); }   // ns = 1 -> clz(0) = 32 -> 0
+
+// `pt` (this lane's point of the tile) against entries [q0, k).  Returns how many of the ns points no entry
+// occludes.  Every lane runs the same number of full steps (unrollable); the ragged last step is predicated.
 template <bool TAIL>
-__device__ __forceinline__ int tight_tile(const float4 *ent, int q0, int k, const float4 *pts, const uint16_t *queue, int ns) {
+__device__ __forceinline__ int tight_tile(const float4 *ent, int q0, int k, const float4 pt, int sh, int ns) {
     const int lane = lane_id();
-    const int sh = 32 - __clz(ns - 1);            // ns = 1 -> clz(0) = 32 -> sh = 0
-    const int G = 1 << sh;
-    const int sidx = lane & (G - 1);
-    const float4 pt = pts[sidx < ns ? (int)queue[sidx] : 0];
     const int kstep = 32 >> sh;
+    int q = q0 + (lane >> sh);
+    const int full = (k - q0) >> (5 - sh);
     bool hit = false;
-#pragma unroll 1
-    for (int q = q0 + (lane >> sh); q < k; q += kstep) {
+#pragma unroll 2
+    for (int t = 0; t < full; ++t, q += kstep) {
         const float4 e = ent[q];
         if (TAIL) hit = hit | (dot_tail(pt.x, pt.y, pt.z, e) <= e.w);
         else hit = hit | (dot_body(pt.x, pt.y, pt.z, e) < e.w);
     }
-    unsigned mk = __ballot_sync(kFull, hit);
-#pragma unroll 1
-    for (int st = 16; st >= G; st >>= 1) mk |= mk >> st;    // OR over the lanes that share a point
+    if (q < k) {
+        const float4 e = ent[q];
+        if (TAIL) hit = hit | (dot_tail(pt.x, pt.y, pt.z, e) <= e.w);
+        else hit = hit | (dot_body(pt.x, pt.y, pt.z, e) < e.w);
+    }
+    // OR over the lanes that share a point: one REDUX.OR of per-point bits
+    const unsigned hm = __reduce_or_sync(kFull, hit ? (1u << (lane & ((1 << sh) - 1))) : 0u);
     const unsigned valid = ns >= 32 ? 0xffffffffu : ((1u << ns) - 1u);
-    return __popc(~mk & valid);
+    return __popc(~hm & valid);
 }
 
 // One atom with its complete neighbour list in ent[0, k), nfront near entries first.  nbody = body points
-// (index < n_body), the tail points are [nbody, n_points).  Returns the exposed-point count.
+// (index < n_body), the tail points are [nbody, n_points); tail_sh = tile_shift(min(32, ntail)).
+// Returns the exposed-point count.
 template <int NSL>
 __device__ __forceinline__ int tight_atom(const KParams &p, const float4 *ent, int k, int nfront, const float4 *pts,
-                                          uint16_t *queue, int nbody) {
+                                          uint16_t *queue, int nbody, int tail_sh) {
     const int lane = lane_id();
     const unsigned lt = lanemask_lt();
     const int m = min(k, min(max(nfront, p.m_min), p.m_max));
@@ -187,7 +193,12 @@ __device__ __forceinline__ int tight_atom(const KParams &p, const float4 *ent, i
         }
         __syncwarp();
 #pragma unroll 1
-        for (int b = 0; b < ns; b += 32) exposed += tight_tile<false>(ent, m, k, pts, queue + b, min(32, ns - b));
+        for (int b = 0; b < ns; b += 32) {
+            const int nb = min(32, ns - b);
+            const int sh = tile_shift(nb);
+            const int sidx = lane & ((1 << sh) - 1);
+            exposed += tight_tile<false>(ent, m, k, pts[sidx < nb ? (int)queue[b + sidx] : 0], sh, nb);
+        }
         __syncwarp();
     }
     const int ntail = (int)p.n_points - nbody;
@@ -195,13 +206,12 @@ __device__ __forceinline__ int tight_atom(const KParams &p, const float4 *ent, i
         if (k == 0) {
             exposed += ntail;
         } else {
+            const int sidx = lane & ((1 << tail_sh) - 1);
 #pragma unroll 1
             for (int t0 = 0; t0 < ntail; t0 += 32) {
                 const int nt = min(32, ntail - t0);
-                if (lane < nt) queue[lane] = (uint16_t)(nbody + t0 + lane);
-                __syncwarp();
-                exposed += tight_tile<true>(ent, 0, k, pts, queue, nt);
-                __syncwarp();
+                // the last batch of a long tail may be narrower than the tile: its surplus lanes re-test point 0
+                exposed += tight_tile<true>(ent, 0, k, pts[nbody + t0 + (sidx < nt ? sidx : 0)], tail_sh, nt);
             }
         }
     }
@@ -248,6 +258,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
     uint16_t *const w_list = reinterpret_cast<uint16_t *>(smem + kOffList) + warp * kListCap;
     stage_points(p, V.ptab);
     const int nbody = (int)min(p.n_points, p.n_body), nsl = (nbody + 31) >> 5;
+    const int tail_sh = tile_shift(max(1, min(32, (int)p.n_points - nbody)));
     const float reach0 = 2.0f * p.probe + kCutSlack;
 
     uint32_t sid, a0;
@@ -283,10 +294,10 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                         const float r = __fadd_rn(ai.w, p.probe);
                         const int nfront = tight_entries(V.atom, ai, p.probe, __fmul_rn(r, r), __fmul_rn(2.0f, r), p.near2,
                                                          w_cand, k, w_ent);
-                        if (nsl == 3) cnt = tight_atom<3>(p, w_ent, k, nfront, V.ptab, w_cand, nbody);
-                        else if (nsl == 4) cnt = tight_atom<4>(p, w_ent, k, nfront, V.ptab, w_cand, nbody);
-                        else if (nsl == 2) cnt = tight_atom<2>(p, w_ent, k, nfront, V.ptab, w_cand, nbody);
-                        else cnt = tight_atom<1>(p, w_ent, k, nfront, V.ptab, w_cand, nbody);
+                        if (nsl == 3) cnt = tight_atom<3>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
+                        else if (nsl == 4) cnt = tight_atom<4>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
+                        else if (nsl == 2) cnt = tight_atom<2>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
+                        else cnt = tight_atom<1>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
                         pairs += (unsigned)k;
                     } else {
                         cnt = tight_cold_atom<HAS_CLS>(p.px, p.py, p.pz, p.n_points, p.n_body, p.probe, p.near2, p.m_min, p.m_max,
