@@ -162,6 +162,28 @@ SASA_B200_API int sasa_b200_batch_run_frames_host(sasa_b200_batch *batch, const 
                                     const sasa_b200_params *params, const sasa_b200_outputs *out,
                                     sasa_b200_stats *stats /* nullable */);
 
+/* Atom-range split of large structures over several GPUs (BASELINE.json config 5: a 1M-atom capsid at 960 points
+ * split across 8 GPUs).  The reference has no counterpart -- its neighbour build is serial and its atom loop is a
+ * rayon par_iter inside one process (src/lib.rs:278-290); this is that par_iter cut across devices.  Every rank
+ * holds ALL atoms of the batch, rebuilds the cell list redundantly (cheaper than exchanging it) and evaluates
+ * only slice `rank` of `n_ranks` of each structure's CELL-SORTED atom order, i.e. a spatially compact slab.
+ * counts / atom_sasa are written for the slice's atoms and ZERO elsewhere, so the element-wise sum over ranks
+ * (ncclAllReduce on the device variant) equals the single-GPU result bit for bit.  Level sums are not produced
+ * here: reduce the summed per-atom vector with sasa_b200_batch_reduce_device or on the host. */
+SASA_B200_API int sasa_b200_batch_run_atom_range_device(sasa_b200_batch *batch, const float *d_xyzr, const uint32_t *d_id_class,
+                                          const sasa_b200_params *params, uint32_t rank, uint32_t n_ranks,
+                                          uint32_t *d_counts /* nullable */, float *d_atom_sasa /* nullable */, void *stream);
+SASA_B200_API int sasa_b200_batch_run_atom_range_host(sasa_b200_batch *batch, const float *xyzr, const uint32_t *id_class,
+                                        const sasa_b200_params *params, uint32_t rank, uint32_t n_ranks,
+                                        uint32_t *out_counts /* nullable */, float *out_atom_sasa /* nullable */,
+                                        sasa_b200_stats *stats /* nullable */);
+
+/* The level sums alone (the numeric part of process_atoms, src/options.rs:195-232, :292-315, :370-410) over a
+ * finished per-atom SASA vector in device memory: d_seg_sasa [n_segments] and d_protein [3*S], both nullable.
+ * One small launch per structure -- meant for the few large structures of the atom-range split. */
+SASA_B200_API int sasa_b200_batch_reduce_device(sasa_b200_batch *batch, const float *d_atom_sasa, float *d_seg_sasa,
+                                  float *d_protein, void *stream);
+
 /* Convenience: create + run_host + destroy. */
 SASA_B200_API int sasa_b200_run_batch(sasa_b200_ctx *ctx, const float *xyzr, const uint32_t *id_class, const uint64_t *struct_off,
                         size_t n_structures, const uint32_t *seg_be, const uint64_t *struct_seg_off,

@@ -21,7 +21,8 @@ EXPORTS = [
     "sasa_b200_alloc_pinned", "sasa_b200_free_pinned", "sasa_b200_sphere_points",
     "sasa_b200_calculate_sasa_internal", "sasa_b200_batch_create", "sasa_b200_batch_destroy",
     "sasa_b200_batch_run_host", "sasa_b200_batch_run_device", "sasa_b200_batch_sync",
-    "sasa_b200_batch_run_frames_host", "sasa_b200_run_batch",
+    "sasa_b200_batch_run_frames_host", "sasa_b200_run_batch", "sasa_b200_batch_run_atom_range_device",
+    "sasa_b200_batch_run_atom_range_host", "sasa_b200_batch_reduce_device",
 ]
 
 
@@ -75,6 +76,10 @@ def load() -> C.CDLL:
     L.sasa_b200_batch_run_device.argtypes = [vp, vp, vp, C.POINTER(Params), C.POINTER(Outputs), vp]
     L.sasa_b200_batch_sync.argtypes = [vp, C.POINTER(Stats)]
     L.sasa_b200_batch_run_frames_host.argtypes = [vp, vp, vp, C.POINTER(Params), C.POINTER(Outputs), C.POINTER(Stats)]
+    L.sasa_b200_batch_run_atom_range_device.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.sasa_b200_batch_run_atom_range_host.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, C.c_uint32, vp, vp,
+                                                      C.POINTER(Stats)]
+    L.sasa_b200_batch_reduce_device.argtypes = [vp, vp, vp, vp, vp]
     L.sasa_b200_run_batch.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, C.POINTER(Params), C.POINTER(Outputs),
                                       C.POINTER(Stats)]
     for name in EXPORTS:

@@ -722,6 +722,114 @@ int sasa_b200_batch_run_frames_host(sasa_b200_batch *b, const float *xyz, const 
     return run_host_impl(b, nullptr, xyz, radii, nullptr, params, out, stats);
 }
 
+// Atom-range split (BASELINE cfg5): every structure of the batch goes through the global-cell-list path and only
+// slice `rank` of `n_ranks` of its cell-sorted atom order is evaluated.  Outputs are zero-filled first, so summing
+// the per-rank vectors (ncclAllReduce over NVLink, or on the host) reproduces the single-GPU result bit for bit.
+static int run_atom_range_locked(sasa_b200_batch *b, const float *d_xyzr, const uint32_t *d_cls, const sasa_b200_params *params,
+                                 uint32_t rank, uint32_t n_ranks, uint32_t *d_counts, float *d_atom, cudaStream_t st) {
+    sasa_b200_ctx *ctx = b->ctx;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    if (n_ranks == 0 || rank >= n_ranks) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "rank %u out of range (%u ranks)", rank, n_ranks);
+    if (params->flags & (SASA_B200_FLAG_BOUNDARY_STATS | SASA_B200_FLAG_FORCE_STREAMING))
+        return fail(ctx, SASA_B200_ERR_UNSUPPORTED, "statistics flags are not available in the atom-range split");
+    uint32_t max_atoms = 0;
+    for (size_t s = 0; s < b->S; ++s) max_atoms = std::max(max_atoms, b->h_off[s + 1] - b->h_off[s]);
+    if (max_atoms && (rc = large_reserve(b->large, max_atoms)) != 0)
+        return fail(ctx, rc, "allocating the large-structure workspace (%u atoms) failed", max_atoms);
+    RunArgs ra;
+    ra.d_xyzr = reinterpret_cast<const float4 *>(d_xyzr);
+    ra.d_cls = d_cls;
+    ra.d_out = sasa_b200_outputs{d_counts, d_atom, nullptr, nullptr};
+    ra.prm = *params;
+    if ((rc = get_points(ctx, params->n_points, &ra.d_points)) != 0) return rc;
+    KParams kp;
+    make_kparams(b, ra, &kp);
+    kp.seg_be = nullptr;
+    kp.out_seg = nullptr;
+    b->launches_last = 0;
+    if (d_counts && b->n_atoms) CU_TRY(ctx, cudaMemsetAsync(d_counts, 0, b->n_atoms * sizeof(uint32_t), st));
+    if (d_atom && b->n_atoms) CU_TRY(ctx, cudaMemsetAsync(d_atom, 0, b->n_atoms * sizeof(float), st));
+    std::vector<uint32_t> order(b->S);
+    std::iota(order.begin(), order.end(), 0u);
+    rc = large_enqueue(ctx->sm_count, b->large, kp, order.data(), (uint32_t)b->S, b->h_off.data(), st, &b->launches_last, rank, n_ranks);
+    if (rc != 0) return fail(ctx, rc, "large-structure path failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return SASA_B200_OK;
+}
+
+int sasa_b200_batch_run_atom_range_device(sasa_b200_batch *b, const float *d_xyzr, const uint32_t *d_id_class,
+                                          const sasa_b200_params *params, uint32_t rank, uint32_t n_ranks,
+                                          uint32_t *d_counts, float *d_atom_sasa, void *stream) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    sasa_b200_ctx *ctx = b->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!d_xyzr && b->n_atoms) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "d_xyzr is NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    return run_atom_range_locked(b, d_xyzr, d_id_class, params, rank, n_ranks, d_counts, d_atom_sasa,
+                                 stream ? (cudaStream_t)stream : ctx->streams[0]);
+}
+
+int sasa_b200_batch_run_atom_range_host(sasa_b200_batch *b, const float *xyzr, const uint32_t *id_class,
+                                        const sasa_b200_params *params, uint32_t rank, uint32_t n_ranks,
+                                        uint32_t *out_counts, float *out_atom_sasa, sasa_b200_stats *stats) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    sasa_b200_ctx *ctx = b->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!xyzr && b->n_atoms) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "xyzr is NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t N = b->n_atoms;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_xyzr = 0, o_cls = al(N * 16), o_cnt = o_cls + (id_class ? al(N * 4) : 0), o_atom = o_cnt + al(N * 4);
+    int rc = arena_reserve(ctx, o_atom + al(N * 4) + 256);
+    if (rc) return rc;
+    char *base_p = static_cast<char *>(ctx->arena);
+    cudaStream_t st = ctx->streams[0];
+    if (N) {
+        CU_TRY(ctx, cudaMemcpyAsync(base_p + o_xyzr, xyzr, N * 16, cudaMemcpyHostToDevice, st));
+        if (id_class) CU_TRY(ctx, cudaMemcpyAsync(base_p + o_cls, id_class, N * 4, cudaMemcpyHostToDevice, st));
+    }
+    rc = run_atom_range_locked(b, reinterpret_cast<const float *>(base_p + o_xyzr),
+                               id_class ? reinterpret_cast<const uint32_t *>(base_p + o_cls) : nullptr, params, rank, n_ranks,
+                               reinterpret_cast<uint32_t *>(base_p + o_cnt), reinterpret_cast<float *>(base_p + o_atom), st);
+    if (rc) return rc;
+    if (N && out_counts) CU_TRY(ctx, cudaMemcpyAsync(out_counts, base_p + o_cnt, N * 4, cudaMemcpyDeviceToHost, st));
+    if (N && out_atom_sasa) CU_TRY(ctx, cudaMemcpyAsync(out_atom_sasa, base_p + o_atom, N * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    b->last = sasa_b200_stats{};
+    rc = finish_run(b, stats);
+    cudaMemset(ctx->d_err, 0, sizeof(int));
+    cudaMemset(ctx->d_stat, 0, 3 * sizeof(unsigned long long));
+    return rc;
+}
+
+int sasa_b200_batch_reduce_device(sasa_b200_batch *b, const float *d_atom_sasa, float *d_seg_sasa, float *d_protein, void *stream) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    sasa_b200_ctx *ctx = b->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!d_atom_sasa && b->n_atoms) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "d_atom_sasa is NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->streams[0];
+    KParams kp;
+    memset(&kp, 0, sizeof kp);
+    kp.struct_off = b->d_off;
+    kp.seg_be = b->d_seg_be;
+    kp.struct_seg_off = b->d_seg_off;
+    kp.seg_polar = b->d_polar;
+    kp.out_seg = b->n_seg ? d_seg_sasa : nullptr;
+    kp.out_protein = d_protein;
+    b->launches_last = 0;
+    for (size_t s = 0; s < b->S; ++s) {
+        const uint32_t a0 = b->h_off[s];
+        const int N = (int)(b->h_off[s + 1] - a0);
+        const uint32_t nseg = b->h_seg_off.empty() ? 0 : b->h_seg_off[s + 1] - b->h_seg_off[s];
+        const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->sm_count, (nseg + 255) / 256 + 1));
+        large_sums_kernel<<<grid, 256, 0, st>>>(kp, (uint32_t)s, N, d_atom_sasa + a0, nullptr);
+        ++b->launches_last;
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    return SASA_B200_OK;
+}
+
 int sasa_b200_run_batch(sasa_b200_ctx *ctx, const float *xyzr, const uint32_t *id_class, const uint64_t *struct_off,
                         size_t S, const uint32_t *seg_be, const uint64_t *struct_seg_off, const uint8_t *seg_polar,
                         const sasa_b200_params *params, const sasa_b200_outputs *out, sasa_b200_stats *stats) {

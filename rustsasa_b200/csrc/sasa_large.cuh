@@ -41,10 +41,10 @@ __device__ __forceinline__ float dec_f(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-__global__ void large_init_kernel(LargeHeader *h) {
+__global__ void large_init_kernel(LargeHeader *h, unsigned first_atom) {
     if (threadIdx.x < 3) h->enc[threadIdx.x] = 0xffffffffu;          // running minima
     else if (threadIdx.x < 8) h->enc[threadIdx.x] = 0u;              // running maxima, flag
-    if (threadIdx.x == 0) h->next_atom = 0u;
+    if (threadIdx.x == 0) h->next_atom = first_atom;
 }
 
 __global__ void __launch_bounds__(256) large_bounds_kernel(const float4 *__restrict__ at, int N, LargeHeader *h) {
@@ -216,8 +216,9 @@ __global__ void __launch_bounds__(256) large_scatter_kernel(const float4 *__rest
     }
 }
 
-// One warp per atom; warps pull consecutive cell-sorted atoms from a global counter so that the warps of
-// a CTA share candidate cells in L1.
+// One warp per atom; warps pull consecutive cell-sorted atoms from a global counter (which starts at the first
+// position of this launch's range) so that the warps of a CTA share candidate cells in L1.  Only sorted positions
+// below N are evaluated: N = the structure's atom count, or the end of this rank's slice in the atom-range split.
 __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, int N, uint32_t a0, LargeHeader *h,
                                                              const float4 *__restrict__ sorted, const uint32_t *__restrict__ orig,
                                                              const uint32_t *__restrict__ cls_sorted, const uint32_t *__restrict__ cells,
@@ -303,7 +304,7 @@ constexpr uint32_t kSeqSumMax = 16384;  // longer ranges are summed by a warp (o
 // atom order like simd_sum (src/utils.rs:14-22); longer ones by a warp-shuffle tree.
 __global__ void __launch_bounds__(256) large_sums_kernel(const KParams p, uint32_t sid, int N, const float *val,
                                                          const LargeHeader *h) {
-    const bool bad = h->ncell == 0 && N > 0;
+    const bool bad = h != nullptr && h->ncell == 0 && N > 0;   // h == nullptr: stand-alone reduction of finished values
     const float qn = __int_as_float(0x7fc00000);
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int gwarp = gtid >> 5, nwarp = nth >> 5;
@@ -394,8 +395,11 @@ inline int large_reserve(LargeWorkspace &w, uint32_t n_atoms) {
 }
 
 // Enqueue the whole pipeline for each large structure of one launch group.  `order` / `off` are host arrays.
+// range_n > 1 selects the atom-range split (BASELINE cfg5): the cell list is built for the whole structure, but
+// only slice `range_rank` of `range_n` of the cell-sorted atom order is evaluated, and no sums are produced.
 inline int large_enqueue(int sm_count, LargeWorkspace &w, const KParams &kp, const uint32_t *order, uint32_t n_work,
-                         const uint32_t *off, cudaStream_t st, uint32_t *launches) {
+                         const uint32_t *off, cudaStream_t st, uint32_t *launches, uint32_t range_rank = 0,
+                         uint32_t range_n = 1) {
     for (uint32_t q = 0; q < n_work; ++q) {
         const uint32_t sid = order[q];
         const uint32_t a0 = off[sid];
@@ -405,7 +409,8 @@ inline int large_enqueue(int sm_count, LargeWorkspace &w, const KParams &kp, con
         const uint32_t *cls = kp.cls ? kp.cls + a0 : nullptr;
         const int gb = std::min((N + 255) / 256, sm_count * 8);
         const int cell_blocks = (int)((w.cap_cells + kScanItems - 1) / kScanItems);
-        large_init_kernel<<<1, 32, 0, st>>>(w.hdr);
+        const uint32_t lo = (uint32_t)((uint64_t)N * range_rank / range_n), hi = (uint32_t)((uint64_t)N * (range_rank + 1) / range_n);
+        large_init_kernel<<<1, 32, 0, st>>>(w.hdr, lo);
         large_bounds_kernel<<<gb, 256, 0, st>>>(at, N, w.hdr);
         large_grid_kernel<<<1, 32, 0, st>>>(w.hdr, kp.probe, w.cap_cells, kp.err_flag);
         large_zero_kernel<<<sm_count * 4, 256, 0, st>>>(w.hdr, w.cells);
@@ -414,17 +419,13 @@ inline int large_enqueue(int sm_count, LargeWorkspace &w, const KParams &kp, con
         large_scan2_kernel<<<1, 1024, 0, st>>>(w.hdr, w.blocksum);
         large_scan3_kernel<<<cell_blocks, 256, 0, st>>>(w.hdr, w.cells, w.blocksum, (uint32_t)N);
         large_scatter_kernel<<<gb, 256, 0, st>>>(at, cls, N, w.hdr, w.cells, w.cellid, w.rank, w.sorted, w.orig, w.cls_sorted);
-        const int ga = std::min((N + 7) / 8, sm_count * 2);
-        large_atoms_kernel<<<ga, 256, 0, st>>>(kp, N, a0, w.hdr, w.sorted, w.orig, cls ? w.cls_sorted : nullptr, w.cells, w.val);
+        const int ga = std::max(1, std::min((int)(hi - lo + 7) / 8, sm_count * 2));
+        large_atoms_kernel<<<ga, 256, 0, st>>>(kp, (int)hi, a0, w.hdr, w.sorted, w.orig, cls ? w.cls_sorted : nullptr, w.cells, w.val);
         *launches += 10;
-        if ((kp.seg_be && kp.out_seg) || kp.out_protein) {
-            large_sums_kernel<<<sm_count, 256, 0, st>>>(kp, sid, N, w.val, w.hdr);
-            ++*launches;
-        } else {
-            // still needed to blank the outputs of a structure with non-finite input
-            large_sums_kernel<<<sm_count, 256, 0, st>>>(kp, sid, N, w.val, w.hdr);
-            ++*launches;
-        }
+        // level sums; also blanks the outputs of a structure with non-finite input (kp carries no segments and
+        // no protein output in the atom-range split, where the per-atom values of other ranks are missing)
+        large_sums_kernel<<<sm_count, 256, 0, st>>>(kp, sid, N, w.val, w.hdr);
+        ++*launches;
         if (cudaGetLastError() != cudaSuccess) return 2;
     }
     return 0;

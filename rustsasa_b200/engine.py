@@ -207,6 +207,34 @@ class Batch:
         self.engine._check(self._L.sasa_b200_batch_run_device(self._h, _ptr(d_xyzr), _ptr(d_id_class), C.byref(prm),
                                                              C.byref(outs), stream or None))
 
+    def run_atom_range_device(self, d_xyzr, rank: int, n_ranks: int, d_id_class=None, probe_radius=1.4, n_points=100,
+                              simd_lanes=8, counts=None, atom_sasa=None, stream: int = 0):
+        """Atom-range split (cfg5): slice `rank` of `n_ranks` of every structure's cell-sorted atom order; the
+        output tensors are zero outside the slice, ready for an all-reduce(SUM) across ranks."""
+        prm = self._params(probe_radius, n_points, simd_lanes, 0)
+        self.engine._check(self._L.sasa_b200_batch_run_atom_range_device(
+            self._h, _ptr(d_xyzr), _ptr(d_id_class), C.byref(prm), rank, n_ranks, _ptr(counts), _ptr(atom_sasa),
+            stream or None))
+
+    def run_atom_range_host(self, xyzr, rank: int, n_ranks: int, id_class=None, probe_radius=1.4, n_points=100,
+                            simd_lanes=8) -> BatchResult:
+        xyzr = _np(xyzr, np.float32, (-1, 4))
+        assert xyzr.shape[0] == self.n_atoms, "xyzr does not match struct_off"
+        id_class = _np(id_class, np.uint32)
+        res = BatchResult(counts=np.zeros(self.n_atoms, np.uint32), atom_sasa=np.zeros(self.n_atoms, np.float32))
+        prm = self._params(probe_radius, n_points, simd_lanes, 0)
+        st = _lib.Stats()
+        self.engine._check(self._L.sasa_b200_batch_run_atom_range_host(
+            self._h, _ptr(xyzr), _ptr(id_class), C.byref(prm), rank, n_ranks, _ptr(res.counts), _ptr(res.atom_sasa),
+            C.byref(st)))
+        res.stats = st.as_dict()
+        return res
+
+    def reduce_device(self, d_atom_sasa, seg_sasa=None, protein=None, stream: int = 0):
+        """Level sums of a finished per-atom SASA vector (torch CUDA tensors)."""
+        self.engine._check(self._L.sasa_b200_batch_reduce_device(self._h, _ptr(d_atom_sasa), _ptr(seg_sasa), _ptr(protein),
+                                                                stream or None))
+
     def sync(self) -> dict:
         st = _lib.Stats()
         self.engine._check(self._L.sasa_b200_batch_sync(self._h, C.byref(st)))

@@ -379,3 +379,62 @@ def test_options_api_process_many(eng, tmp_path):
     assert all(isinstance(o, SASACalcError) and o.kind == "RadiusMissing" for o in out)
     ok = SASAOptions(AtomLevel).with_include_hydrogens(True).with_allow_vdw_fallback(True).process(st, eng)
     assert ok.shape == (12,)
+
+
+def test_atom_range_split_sums_to_single_gpu(eng, golden):
+    """cfg5 mechanics on one GPU: the per-rank partial vectors are disjoint and their sum is the full result."""
+    import torch
+    from rustsasa_b200 import workloads as W
+    a = W.large_assembly(30000)
+    b = eng.batch(a.struct_off, a.seg_be, a.struct_seg_off, a.seg_polar)
+    full = b.run_host(a.xyzr)
+    parts = [b.run_atom_range_host(a.xyzr, r, 3) for r in range(3)]
+    touched = sum((p.atom_sasa != 0) | (p.counts != 0) for p in parts)
+    assert touched.max() == 1
+    sizes = [int(((p.atom_sasa != 0) | (p.counts != 0)).sum()) for p in parts]
+    assert max(sizes) - min(sizes) < 0.2 * a.n_atoms / 3          # slices of the sorted order are near-equal
+    counts = parts[0].counts + parts[1].counts + parts[2].counts
+    atom = parts[0].atom_sasa + parts[1].atom_sasa + parts[2].atom_sasa
+    assert np.array_equal(counts, full.counts) and np.array_equal(atom, full.atom_sasa)
+    d_atom = torch.from_numpy(atom).cuda()
+    d_seg = torch.zeros(len(a.seg_be), dtype=torch.float32, device="cuda")
+    d_prot = torch.zeros(3, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    b.reduce_device(d_atom, d_seg, d_prot)
+    b.sync()
+    assert np.array_equal(d_seg.cpu().numpy(), full.seg_sasa)
+    assert close_enough(d_prot.cpu().numpy(), full.protein[0])
+    b.close()
+    # several (small) structures in one range-mode batch, with id classes, 960 points
+    structs = [golden.structure(n) for n in ("example.cif", "2drt")]
+    xyzr, off, seg, soff, pol = _concat(structs)
+    b = eng.batch(off, seg, soff, pol)
+    full = b.run_host(xyzr, n_points=960, want=("counts", "atom"))
+    parts = [b.run_atom_range_host(xyzr, r, 2, n_points=960) for r in range(2)]
+    assert np.array_equal(parts[0].counts + parts[1].counts, full.counts)
+    assert np.array_equal(parts[0].atom_sasa + parts[1].atom_sasa, full.atom_sasa)
+    from rustsasa_b200 import SasaB200Error
+    with pytest.raises(SasaB200Error):
+        b.run_atom_range_host(xyzr, 2, 2)
+    b.close()
+
+
+def test_sharded_run_matches_single(eng):
+    """The multi-GPU sharding path (rustsasa_b200.shard) with the real engine: shards run one after another on
+    this GPU and reassembled equal the unsharded batch."""
+    from rustsasa_b200 import workloads as W
+    from rustsasa_b200.shard import partition_structures, run_sharded, take_shard
+    d = W.proteome_batch(40)
+
+    def compute(sh):
+        bb = eng.batch(sh.struct_off, sh.seg_be, sh.struct_seg_off, sh.seg_polar)
+        try:
+            return bb.run_host(sh.xyzr, sh.id_class)
+        finally:
+            bb.close()
+    whole = run_sharded(compute, d.xyzr, d.struct_off, d.seg_be, d.struct_seg_off, d.seg_polar, rank=0, world=1)
+    bounds = partition_structures(d.struct_off, 3)
+    pieces = [compute(take_shard(bounds, r, d.xyzr, d.struct_off, d.seg_be, d.struct_seg_off, d.seg_polar)) for r in range(3)]
+    assert np.array_equal(np.concatenate([p.counts for p in pieces]), whole.counts)
+    assert np.array_equal(np.concatenate([p.seg_sasa for p in pieces]), whole.seg_sasa)
+    assert np.array_equal(np.concatenate([p.protein for p in pieces]), whole.protein)
