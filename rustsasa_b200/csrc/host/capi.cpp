@@ -1,0 +1,93 @@
+// capi.cpp -- small extern "C" surface over the C++ host layer so that the Python test-suite can exercise it
+// (extraction parity against rustsasa_b200/structure.py on CPU, end-to-end JSON on the GPU box).
+#include <cstring>
+
+#include "../../../include/sasa_b200.hpp"
+
+using namespace rust_sasa;
+
+namespace {
+void put_error(char *err, size_t n, const std::string &msg) {
+    if (err && n) {
+        std::strncpy(err, msg.c_str(), n - 1);
+        err[n - 1] = '\0';
+    }
+}
+OptionValues make_opts(float probe, size_t n_points, int include_h, int include_het, int vdw_fallback, int occ_radii,
+                       const char *radii_file) {
+    OptionValues o;
+    o.probe_radius = probe;
+    o.n_points = n_points;
+    o.include_hydrogens = include_h != 0;
+    o.include_hetatms = include_het != 0;
+    o.allow_vdw_fallback = vdw_fallback != 0;
+    o.read_radii_from_occupancy = occ_radii != 0;
+    if (radii_file && *radii_file) o.radii_config = std::make_shared<const RadiiConfig>(load_radii_from_file(radii_file));
+    return o;
+}
+}  // namespace
+
+#define HOST_API extern "C" __attribute__((visibility("default")))
+
+HOST_API void *sasa_b200_host_pack(const char *path, int level, int include_h, int include_het, int vdw_fallback, int occ_radii,
+                                   const char *radii_file, char *err, size_t errlen) {
+    try {
+        const OptionValues o = make_opts(1.4f, 100, include_h, include_het, vdw_fallback, occ_radii, radii_file);
+        return new Packed(build_atoms_and_mapping(pdb::open(path), (LevelKind)level, o));
+    } catch (const SASACalcError &e) {
+        put_error(err, errlen, std::string(e.kind_name()) + ": " + e.what());
+    } catch (const std::exception &e) {
+        put_error(err, errlen, std::string("IO: ") + e.what());
+    }
+    return nullptr;
+}
+HOST_API size_t sasa_b200_host_pack_atoms(const void *p) { return static_cast<const Packed *>(p)->n_atoms(); }
+HOST_API size_t sasa_b200_host_pack_segments(const void *p) { return static_cast<const Packed *>(p)->seg_polar.size(); }
+HOST_API void sasa_b200_host_pack_copy(const void *h, float *xyzr, uint64_t *ids, uint32_t *seg_be, uint8_t *polar) {
+    const Packed &p = *static_cast<const Packed *>(h);
+    if (xyzr) std::memcpy(xyzr, p.xyzr.data(), p.xyzr.size() * 4);
+    if (ids) std::memcpy(ids, p.ids.data(), p.ids.size() * 8);
+    if (seg_be) std::memcpy(seg_be, p.seg_be.data(), p.seg_be.size() * 4);
+    if (polar) std::memcpy(polar, p.seg_polar.data(), p.seg_polar.size());
+}
+HOST_API void sasa_b200_host_pack_free(void *p) { delete static_cast<Packed *>(p); }
+
+// path -> SASAOptions<level>::process -> JSON text (needs the GPU).  Returns the JSON length, or -1 with err filled.
+HOST_API long sasa_b200_host_process_json(const char *path, int level, float probe, size_t n_points, int include_h, int include_het,
+                                          int vdw_fallback, int occ_radii, const char *radii_file, char *out, size_t outlen, char *err,
+                                          size_t errlen) {
+    try {
+        const OptionValues o = make_opts(probe, n_points, include_h, include_het, vdw_fallback, occ_radii, radii_file);
+        const pdb::PDB st = pdb::open(path);
+        auto res = process_many({&st}, (LevelKind)level, o);
+        if (auto *e = std::get_if<SASACalcError>(&res[0])) throw *e;
+        const std::string js = sasa_result_to_json(std::get<SASAResult>(res[0]));
+        if (js.size() + 1 > outlen) {
+            put_error(err, errlen, "IO: output buffer too small");
+            return -1;
+        }
+        std::memcpy(out, js.c_str(), js.size() + 1);
+        return (long)js.size();
+    } catch (const SASACalcError &e) {
+        put_error(err, errlen, std::string(e.kind_name()) + ": " + e.what());
+    } catch (const std::exception &e) {
+        put_error(err, errlen, std::string("IO: ") + e.what());
+    }
+    return -1;
+}
+
+// writers on hand-made values (CPU-only formatting tests): kind 0 atom, 3 protein
+HOST_API long sasa_b200_host_format(int xml, int kind, const float *values, size_t n, char *out, size_t outlen) {
+    SASAResult r;
+    if (kind == 3 && n >= 3) r = ProteinResult{values[0], values[1], values[2]};
+    else r = std::vector<float>(values, values + n);
+    const std::string s = xml ? sasa_result_to_xml(r) : sasa_result_to_json(r);
+    if (s.size() + 1 > outlen) return -1;
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return (long)s.size();
+}
+HOST_API long sasa_b200_host_serialize_chain_id(const char *s) { return (long)serialize_chain_id(s); }
+HOST_API float sasa_b200_host_get_radius(const char *res, const char *atom) {
+    auto r = get_radius(res, atom, nullptr);
+    return r ? *r : -1.0f;
+}

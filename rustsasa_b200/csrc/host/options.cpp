@@ -1,0 +1,294 @@
+// options.cpp -- the level API over the C ABI: atom extraction (row A0), the batched engine call, and the mapping of
+// its outputs back to the reference's result structs.
+//
+//   build_atoms_and_mapping   src/options.rs:151-189 (Atom), :234-287 (Residue), :317-365 (Chain), :412-464 (Protein),
+//                             build_atom! :81-116, get_radius src/utils.rs:40-56, combine_hash src/utils.rs:83-87
+//   process / process_many    src/options.rs:606-618; directory mode src/main.rs:342-480
+//   calculate_sasa_internal   src/lib.rs:249-298
+// The numeric part of process_atoms (sequential f32 sums per residue / chain / protein) runs on the GPU inside the
+// same launch (seg_sasa / protein outputs of sasa_b200_batch_run_host); strings and metadata stay here.
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "../../../include/sasa_b200.h"
+#include "../../../include/sasa_b200.hpp"
+
+namespace rust_sasa {
+
+namespace {
+
+// Alvarez (2013) van der Waals radii as tabulated by pdbtbx/src/structs/elements.rs:631-647 ff.
+const std::unordered_map<std::string, float> &vdw_radii() {
+    static const std::unordered_map<std::string, float> t = {
+        {"H", 1.2f},   {"HE", 1.43f}, {"LI", 2.12f}, {"BE", 1.98f}, {"B", 1.91f},  {"C", 1.77f},  {"N", 1.66f},  {"O", 1.5f},
+        {"F", 1.46f},  {"NE", 1.58f}, {"NA", 2.5f},  {"MG", 2.51f}, {"AL", 2.25f}, {"SI", 2.19f}, {"P", 1.9f},   {"S", 1.89f},
+        {"CL", 1.82f}, {"AR", 1.83f}, {"K", 2.73f},  {"CA", 2.62f}, {"SC", 2.58f}, {"TI", 2.46f}, {"V", 2.42f},  {"CR", 2.45f},
+        {"MN", 2.45f}, {"FE", 2.44f}, {"CO", 2.4f},  {"NI", 2.4f},  {"CU", 2.38f}, {"ZN", 2.39f}, {"GA", 2.32f}, {"GE", 2.29f},
+        {"AS", 1.88f}, {"SE", 1.82f}, {"BR", 1.86f}, {"KR", 2.25f}};
+    return t;
+}
+
+// FNV-1a over the bytes Rust's `(&str, usize).hash()` feeds the hasher: the string bytes, a 0xff terminator, then the
+// usize in little-endian order (src/utils.rs:83-87).  Only equality of ids is observable on the path.
+std::uint64_t atom_id_hash(const std::string &altloc, std::size_t serial) {
+    std::uint64_t h = 0xcbf29ce484222325ull;
+    auto feed = [&h](unsigned char b) { h = (h ^ b) * 0x100000001b3ull; };
+    for (unsigned char c : altloc) feed(c);
+    feed(0xff);
+    for (int i = 0; i < 8; ++i) feed((unsigned char)((std::uint64_t)serial >> (8 * i)));
+    return h;
+}
+
+int g_device = -1;
+std::mutex g_ctx_mu;
+sasa_b200_ctx *g_ctx = nullptr;
+
+sasa_b200_ctx *context() {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (g_ctx) return g_ctx;
+    int device = g_device;
+    if (device < 0) {
+        const char *e = std::getenv("SASA_B200_DEVICE");
+        device = e ? std::atoi(e) : 0;
+    }
+    if (sasa_b200_create(device, &g_ctx) != SASA_B200_OK) {
+        g_ctx = nullptr;
+        throw SASACalcError(SASACalcError::Kind::Device, std::string("sasa_b200_create failed: ") + sasa_b200_last_error(nullptr));
+    }
+    return g_ctx;
+}
+
+[[noreturn]] void throw_device(sasa_b200_ctx *ctx, const char *what) {
+    throw SASACalcError(SASACalcError::Kind::Device, std::string(what) + ": " + sasa_b200_last_error(ctx));
+}
+
+// Dense equality classes of the ids of one structure, or empty when all ids are distinct.
+std::vector<std::uint32_t> id_classes(const std::vector<std::uint64_t> &ids, std::uint32_t base) {
+    std::unordered_map<std::uint64_t, std::uint32_t> rank;
+    rank.reserve(ids.size() * 2);
+    std::vector<std::uint32_t> cls(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) cls[i] = base + rank.emplace(ids[i], (std::uint32_t)rank.size()).first->second;
+    if (rank.size() == ids.size()) cls.clear();
+    return cls;
+}
+
+}  // namespace
+
+void set_device(int device) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    g_device = device;
+}
+
+// ---- row A0 ---------------------------------------------------------------------------------------------------------
+Packed build_atoms_and_mapping(const pdb::PDB &pdb, LevelKind level, const OptionValues &opt) {
+    Packed out;
+    const RadiiConfig *custom = opt.radii_config.get();
+    auto push = [&](const pdb::AtomRec &a, const std::string &resname, const std::string &altloc) {
+        if (a.element.empty()) throw SASACalcError(SASACalcError::Kind::ElementMissing, "Element missing for atom");
+        if (a.element == "H" && !opt.include_hydrogens) return;
+        if (a.hetero && !opt.include_hetatms) return;
+        float radius;
+        if (opt.read_radii_from_occupancy) {
+            radius = (float)a.occupancy;
+        } else if (auto r = get_radius(resname, a.name, custom)) {
+            radius = *r;
+        } else if (opt.allow_vdw_fallback) {
+            auto it = vdw_radii().find(a.element);
+            if (it == vdw_radii().end())
+                throw SASACalcError(SASACalcError::Kind::VanDerWaalsMissing, "Van der Waals radius missing for element");
+            radius = it->second;
+        } else {
+            throw SASACalcError(SASACalcError::Kind::RadiusMissing, "Radius not found for residue '" + resname + "' atom '" + a.name +
+                                                                        "' of type '" + a.element + "'.");
+        }
+        out.xyzr.push_back((float)a.x);
+        out.xyzr.push_back((float)a.y);
+        out.xyzr.push_back((float)a.z);
+        out.xyzr.push_back(radius);
+        out.ids.push_back(atom_id_hash(altloc, a.serial));
+    };
+    auto residue_name = [](const pdb::Residue &r) {
+        auto n = r.name();
+        if (!n && !r.conformers.empty())
+            throw SASACalcError(SASACalcError::Kind::FailedToGetResidueName, "Failed to get residue name");
+        return n;
+    };
+
+    if (level == LevelKind::Atom) {
+        for (const pdb::Model &m : pdb.models)
+            for (const pdb::Chain &c : m.chains)
+                for (const pdb::Residue &r : c.residues) {
+                    auto name = residue_name(r);
+                    if (r.conformers.empty()) continue;
+                    const pdb::Conformer &conf = r.conformers[0];   // first conformer only (src/options.rs:255)
+                    for (const pdb::AtomRec &a : conf.atoms) push(a, *name, conf.altloc);
+                }
+        return out;
+    }
+
+    // key -> range with HashMap::insert semantics (last writer wins), then one segment per hierarchy element in order
+    std::map<std::string, std::pair<std::uint32_t, std::uint32_t>> key_range;
+    std::vector<std::string> seg_keys;
+    for (const pdb::Model &m : pdb.models)
+        for (const pdb::Chain &c : m.chains) {
+            const std::uint32_t chain_begin = (std::uint32_t)out.n_atoms();
+            for (const pdb::Residue &r : c.residues) {
+                auto name = residue_name(r);
+                const std::uint32_t begin = (std::uint32_t)out.n_atoms();
+                const std::string rkey = c.id + "\x1f" + std::to_string(r.serial) + "\x1f" + r.icode;
+                if (!r.conformers.empty()) {
+                    const pdb::Conformer &conf = r.conformers[0];
+                    // ProteinLevel hashes ("", serial) for the atom id (src/options.rs:453)
+                    for (const pdb::AtomRec &a : conf.atoms) push(a, *name, level == LevelKind::Protein ? std::string() : conf.altloc);
+                    if (level != LevelKind::Chain) key_range[rkey] = {begin, (std::uint32_t)out.n_atoms()};
+                }
+                if (level != LevelKind::Chain) {
+                    seg_keys.push_back(rkey);
+                    const std::string nm = name ? *name : std::string();
+                    out.residue_meta.push_back(ResidueResult{r.serial, r.icode, 0.0f, nm, is_polar_residue(nm), c.id});
+                }
+            }
+            if (level == LevelKind::Chain) {
+                const std::string ckey = std::to_string(serialize_chain_id(c.id));   // lossy key, collisions preserved
+                key_range[ckey] = {chain_begin, (std::uint32_t)out.n_atoms()};
+                seg_keys.push_back(ckey);
+                out.chain_meta.push_back(ChainResult{c.id, 0.0f});
+            }
+        }
+    out.seg_be.reserve(2 * seg_keys.size());
+    for (size_t k = 0; k < seg_keys.size(); ++k) {
+        auto it = key_range.find(seg_keys[k]);
+        if (it == key_range.end())
+            throw SASACalcError(SASACalcError::Kind::AtomMapToLevelElementFailed, "Failed to map atoms back to level element");
+        out.seg_be.push_back(it->second.first);
+        out.seg_be.push_back(it->second.second);
+        out.seg_polar.push_back(level != LevelKind::Chain && out.residue_meta[k].is_polar ? 1 : 0);
+    }
+    return out;
+}
+
+// ---- the batched engine call ----------------------------------------------------------------------------------------
+std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &packed, LevelKind level, const OptionValues &opt) {
+    std::vector<ProcessOutcome> results;
+    results.reserve(packed.size());
+    const size_t S = packed.size();
+    std::vector<std::uint64_t> struct_off(S + 1, 0), seg_off(S + 1, 0);
+    for (size_t s = 0; s < S; ++s) {
+        struct_off[s + 1] = struct_off[s] + packed[s]->n_atoms();
+        seg_off[s + 1] = seg_off[s] + packed[s]->seg_polar.size();
+    }
+    const size_t N = struct_off[S], G = seg_off[S];
+    sasa_b200_ctx *ctx = context();
+    // pinned staging: the pipelined host entry point overlaps H2D, kernels and D2H across chunks
+    void *pin = nullptr;
+    const size_t in_bytes = N * 16, out_atom = level == LevelKind::Atom ? N * 4 : 0, out_seg = G * 4, out_prot = S * 12;
+    if (sasa_b200_alloc_pinned(in_bytes + out_atom + out_seg + out_prot + 64, &pin) != SASA_B200_OK) throw_device(nullptr, "alloc_pinned");
+    struct Free { void *p; ~Free() { sasa_b200_free_pinned(p); } } guard{pin};
+    float *h_xyzr = static_cast<float *>(pin);
+    float *h_atom = reinterpret_cast<float *>(static_cast<char *>(pin) + in_bytes);
+    float *h_seg = reinterpret_cast<float *>(static_cast<char *>(pin) + in_bytes + out_atom);
+    float *h_prot = reinterpret_cast<float *>(static_cast<char *>(pin) + in_bytes + out_atom + out_seg);
+    std::vector<std::uint32_t> seg_be(2 * G), id_class;
+    std::vector<std::uint8_t> polar(G);
+    bool any_dup = false;
+    for (size_t s = 0; s < S; ++s) {
+        const Packed &p = *packed[s];
+        if (p.n_atoms()) std::memcpy(h_xyzr + 4 * struct_off[s], p.xyzr.data(), p.n_atoms() * 16);
+        if (!p.seg_polar.empty()) {
+            std::memcpy(seg_be.data() + 2 * seg_off[s], p.seg_be.data(), p.seg_be.size() * 4);
+            std::memcpy(polar.data() + seg_off[s], p.seg_polar.data(), p.seg_polar.size());
+        }
+        std::vector<std::uint32_t> cls = id_classes(p.ids, (std::uint32_t)struct_off[s]);
+        if (!cls.empty()) {
+            if (!any_dup) {   // first structure with duplicate ids: earlier atoms get distinct classes
+                id_class.resize(N);
+                for (size_t i = 0; i < N; ++i) id_class[i] = (std::uint32_t)i;
+                any_dup = true;
+            }
+            std::memcpy(id_class.data() + struct_off[s], cls.data(), cls.size() * 4);
+        }
+    }
+    sasa_b200_batch *batch = nullptr;
+    if (sasa_b200_batch_create(ctx, struct_off.data(), S, G ? seg_be.data() : nullptr, G ? seg_off.data() : nullptr,
+                               G ? polar.data() : nullptr, &batch) != SASA_B200_OK)
+        throw_device(ctx, "batch_create");
+    sasa_b200_params prm{opt.probe_radius, (std::uint32_t)opt.n_points, 8, (std::int32_t)opt.threads, 0};
+    sasa_b200_outputs outs{nullptr, level == LevelKind::Atom ? h_atom : nullptr,
+                           (level == LevelKind::Residue || level == LevelKind::Chain) && G ? h_seg : nullptr,
+                           level == LevelKind::Protein ? h_prot : nullptr};
+    const int rc = sasa_b200_batch_run_host(batch, h_xyzr, any_dup ? id_class.data() : nullptr, &prm, &outs, nullptr);
+    sasa_b200_batch_destroy(batch);
+    if (rc != SASA_B200_OK) throw_device(ctx, "batch_run_host");
+    for (size_t s = 0; s < S; ++s) {
+        const Packed &p = *packed[s];
+        switch (level) {
+            case LevelKind::Atom:
+                results.emplace_back(SASAResult(std::vector<float>(h_atom + struct_off[s], h_atom + struct_off[s + 1])));
+                break;
+            case LevelKind::Residue: {
+                std::vector<ResidueResult> v = p.residue_meta;
+                for (size_t k = 0; k < v.size(); ++k) v[k].value = h_seg[seg_off[s] + k];
+                results.emplace_back(SASAResult(std::move(v)));
+                break;
+            }
+            case LevelKind::Chain: {
+                std::vector<ChainResult> v = p.chain_meta;
+                for (size_t k = 0; k < v.size(); ++k) v[k].value = h_seg[seg_off[s] + k];
+                results.emplace_back(SASAResult(std::move(v)));
+                break;
+            }
+            case LevelKind::Protein:
+                results.emplace_back(SASAResult(ProteinResult{h_prot[3 * s], h_prot[3 * s + 1], h_prot[3 * s + 2]}));
+                break;
+        }
+    }
+    return results;
+}
+
+std::vector<ProcessOutcome> process_many(const std::vector<const pdb::PDB *> &pdbs, LevelKind level, const OptionValues &opt) {
+    std::vector<std::optional<Packed>> packed(pdbs.size());
+    std::vector<std::optional<SASACalcError>> errors(pdbs.size());
+    std::vector<const Packed *> good;
+    for (size_t i = 0; i < pdbs.size(); ++i) {
+        try {
+            packed[i] = build_atoms_and_mapping(*pdbs[i], level, opt);
+            good.push_back(&*packed[i]);
+        } catch (const SASACalcError &e) {
+            errors[i] = e;
+        }
+    }
+    std::vector<ProcessOutcome> computed = good.empty() ? std::vector<ProcessOutcome>() : process_packed(good, level, opt);
+    std::vector<ProcessOutcome> out;
+    out.reserve(pdbs.size());
+    size_t g = 0;
+    for (size_t i = 0; i < pdbs.size(); ++i) {
+        if (errors[i]) out.emplace_back(*errors[i]);
+        else out.emplace_back(std::move(computed[g++]));
+    }
+    return out;
+}
+
+// ---- src/lib.rs:249-298 -----------------------------------------------------------------------------------------------
+std::vector<float> calculate_sasa_internal(const std::vector<Atom> &atoms, float probe_radius, std::size_t n_points,
+                                           std::ptrdiff_t threads) {
+    if (atoms.empty()) return {};   // tests/sanity.rs:148-157
+    std::vector<float> xyzr(4 * atoms.size());
+    std::vector<std::uint64_t> ids(atoms.size());
+    for (size_t i = 0; i < atoms.size(); ++i) {
+        xyzr[4 * i + 0] = atoms[i].position[0];
+        xyzr[4 * i + 1] = atoms[i].position[1];
+        xyzr[4 * i + 2] = atoms[i].position[2];
+        xyzr[4 * i + 3] = atoms[i].radius;
+        ids[i] = (std::uint64_t)atoms[i].id;
+    }
+    std::vector<float> out(atoms.size());
+    sasa_b200_ctx *ctx = context();
+    if (sasa_b200_calculate_sasa_internal(ctx, xyzr.data(), ids.data(), atoms.size(), probe_radius, n_points, threads, out.data(),
+                                          nullptr) != SASA_B200_OK)
+        throw_device(ctx, "calculate_sasa_internal");   // the reference panics on non-finite input
+    return out;
+}
+
+}  // namespace rust_sasa

@@ -1,0 +1,427 @@
+// structure.cpp -- host-side reader and radius tables in front of the hot path.
+//
+// A columnar ATOM/HETATM reader for PDB and mmCIF that reproduces the ordering rules the reference inherits from
+// its pdbtbx fork, because they define the atom order of every per-atom output:
+//   * hierarchy and first-seen ordering      pdbtbx/src/read/pdb/parser.rs:144-251 (chains and residues in
+//     insertion order per model, conformers keyed by (residue name, alt-loc)); serial / residue-number wrap
+//     handling :167-173
+//   * mmCIF columns                           pdbtbx/src/read/mmcif/parser.rs:456-600 (auth_asym_id / auth_seq_id
+//     with label_* fallback, serial number = running atom count per model, hetero from group_PDB, model from
+//     pdbx_PDB_model_num)
+//   * blank alt-loc atoms appended to every other conformer     pdbtbx/src/validate.rs:302-325
+//   * element resolution                      pdbtbx/src/structs/atom.rs:74-87
+// Coordinates are parsed as double and cast to float at extraction, like the reference (f64 as f32).
+// It is not a general structure parser (no symmetry, bonds or validation).
+#include <algorithm>
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <unordered_set>
+
+#include "../../../include/sasa_b200.hpp"
+
+namespace rust_sasa {
+
+// ---- radii ----------------------------------------------------------------------------------------------------
+namespace {
+const char kProtorConfig[] =
+#include "protor_config.inc"
+    ;
+
+std::vector<std::string_view> split_ws(std::string_view s) {
+    std::vector<std::string_view> out;
+    size_t i = 0;
+    while (i < s.size()) {
+        while (i < s.size() && std::isspace((unsigned char)s[i])) ++i;
+        size_t j = i;
+        while (j < s.size() && !std::isspace((unsigned char)s[j])) ++j;
+        if (j > i) out.push_back(s.substr(i, j - i));
+        i = j;
+    }
+    return out;
+}
+
+std::string_view trim(std::string_view s) {
+    while (!s.empty() && std::isspace((unsigned char)s.front())) s.remove_prefix(1);
+    while (!s.empty() && std::isspace((unsigned char)s.back())) s.remove_suffix(1);
+    return s;
+}
+
+std::string upper(std::string_view s) {
+    std::string r(s);
+    for (char &c : r) c = (char)std::toupper((unsigned char)c);
+    return r;
+}
+}  // namespace
+
+// src/utils/consts.rs:31-81: "types:" section maps a type name to a radius, "atoms:" maps (residue, atom) to a type.
+RadiiConfig parse_radii_config(std::string_view content) {
+    std::unordered_map<std::string, float> types;
+    RadiiConfig atoms;
+    enum { None, Types, Atoms } section = None;
+    size_t pos = 0;
+    while (pos <= content.size()) {
+        size_t eol = content.find('\n', pos);
+        if (eol == std::string_view::npos) eol = content.size();
+        std::string_view line = trim(content.substr(pos, eol - pos));
+        pos = eol + 1;
+        if (line.empty() || line[0] == '#' || line.substr(0, 5) == "name:") continue;
+        if (line == "types:") { section = Types; continue; }
+        if (line == "atoms:") { section = Atoms; continue; }
+        auto parts = split_ws(line);
+        if (section == Types && parts.size() >= 2) {
+            char *end = nullptr;
+            std::string v(parts[1]);
+            const float r = std::strtof(v.c_str(), &end);
+            if (end && *end == '\0') types[std::string(parts[0])] = r;
+        } else if (section == Atoms && parts.size() >= 3) {
+            auto it = types.find(std::string(parts[2]));
+            if (it != types.end()) atoms[std::string(parts[0])][std::string(parts[1])] = it->second;
+        }
+    }
+    return atoms;
+}
+
+RadiiConfig load_radii_from_file(const std::string &path) {
+    std::ifstream fh(path);
+    if (!fh) throw SASACalcError(SASACalcError::Kind::RadiiFileLoad, "Failed to load radii file: cannot open " + path);
+    std::stringstream ss;
+    ss << fh.rdbuf();
+    return parse_radii_config(ss.str());
+}
+
+const RadiiConfig &protor_radii() {
+    static const RadiiConfig table = parse_radii_config(kProtorConfig);
+    return table;
+}
+
+std::optional<float> get_protor_radius(const std::string &residue, const std::string &atom) {
+    const auto &t = protor_radii();
+    auto r = t.find(residue);
+    if (r == t.end()) return std::nullopt;
+    auto a = r->second.find(atom);
+    if (a == r->second.end()) return std::nullopt;
+    return a->second;
+}
+
+std::optional<float> get_radius(const std::string &residue, const std::string &atom, const RadiiConfig *custom) {
+    if (custom) {
+        auto r = custom->find(residue);
+        if (r != custom->end()) {
+            auto a = r->second.find(atom);
+            if (a != r->second.end()) return a->second;
+        }
+    }
+    return get_protor_radius(residue, atom);
+}
+
+std::ptrdiff_t serialize_chain_id(std::string_view s) {
+    std::ptrdiff_t result = 0;
+    for (char c : s)
+        if ((unsigned char)c < 128 && std::isalpha((unsigned char)c)) result = result * 10 + (std::toupper((unsigned char)c) - 64);
+    return result;
+}
+
+bool is_polar_residue(const std::string &name) {
+    static const std::unordered_set<std::string> polar = {"SER", "THR", "CYS", "ASN", "GLN", "TYR"};
+    return polar.count(name) != 0;
+}
+
+const char *SASACalcError::kind_name() const {
+    switch (kind_) {
+        case Kind::ElementMissing: return "ElementMissing";
+        case Kind::VanDerWaalsMissing: return "VanDerWaalsMissing";
+        case Kind::RadiusMissing: return "RadiusMissing";
+        case Kind::AtomMapToLevelElementFailed: return "AtomMapToLevelElementFailed";
+        case Kind::FailedToGetResidueName: return "FailedToGetResidueName";
+        case Kind::RadiiFileLoad: return "RadiiFileLoad";
+        case Kind::Device: return "Device";
+    }
+    return "?";
+}
+
+// ---- hierarchy ----------------------------------------------------------------------------------------------------
+namespace pdb {
+
+std::optional<std::string> Residue::name() const {
+    if (conformers.empty()) return std::nullopt;
+    for (const Conformer &c : conformers)
+        if (c.name != conformers[0].name) return std::nullopt;
+    return conformers[0].name;
+}
+
+std::size_t PDB::atom_count() const {
+    std::size_t n = 0;
+    for (const Model &m : models)
+        for (const Chain &c : m.chains)
+            for (const Residue &r : c.residues)
+                for (const Conformer &f : r.conformers) n += f.atoms.size();
+    return n;
+}
+
+namespace {
+
+const std::unordered_set<std::string> &elements() {
+    static const std::unordered_set<std::string> set = [] {
+        const char *all =
+            "H HE LI BE B C N O F NE NA MG AL SI P S CL AR K CA SC TI V CR MN FE CO NI CU ZN GA GE AS SE BR KR RB SR Y ZR "
+            "NB MO TC RU RH PD AG CD IN SN SB TE I XE CS BA LA CE PR ND PM SM EU GD TB DY HO ER TM YB LU HF TA W RE OS IR "
+            "PT AU HG TL PB BI PO AT RN FR RA AC TH PA U NP PU AM CM BK CF ES FM MD NO LR RF DB SG BH HS MT DS RG CN NH FL "
+            "MC LV TS OG";
+        std::unordered_set<std::string> s;
+        for (auto t : split_ws(all)) s.emplace(t);
+        return s;
+    }();
+    return set;
+}
+
+// pdbtbx Atom::new: the element column if it names an element, else the atom name, else its first letter if CHNOS.
+std::string resolve_element(std::string_view element, std::string_view atom_name) {
+    const std::string e = upper(trim(element));
+    if (elements().count(e)) return e;
+    const std::string n = upper(trim(atom_name));
+    if (elements().count(n)) return n;
+    if (!n.empty() && std::strchr("CHNOS", n[0])) return std::string(1, n[0]);
+    return std::string();
+}
+
+void add_atom(Model &model, const std::string &chain_id, std::ptrdiff_t res_serial, const std::string &icode,
+              const std::string &res_name, const std::string &altloc, AtomRec &&atom) {
+    auto ci = model.chain_index.find(chain_id);
+    if (ci == model.chain_index.end()) {
+        ci = model.chain_index.emplace(chain_id, model.chains.size()).first;
+        model.chains.emplace_back();
+        model.chains.back().id = chain_id;
+    }
+    Chain &chain = model.chains[ci->second];
+    const std::string rkey = std::to_string(res_serial) + "|" + icode;
+    auto ri = chain.residue_index.find(rkey);
+    if (ri == chain.residue_index.end()) {
+        ri = chain.residue_index.emplace(rkey, chain.residues.size()).first;
+        chain.residues.emplace_back();
+        chain.residues.back().serial = res_serial;
+        chain.residues.back().icode = icode;
+    }
+    Residue &res = chain.residues[ri->second];
+    Conformer *conf = nullptr;
+    for (Conformer &c : res.conformers)
+        if (c.name == res_name && c.altloc == altloc) { conf = &c; break; }
+    if (!conf) {
+        res.conformers.emplace_back();
+        conf = &res.conformers.back();
+        conf->name = res_name;
+        conf->altloc = altloc;
+    }
+    conf->atoms.push_back(std::move(atom));
+    ++model.atom_count;
+}
+
+// pdbtbx/src/validate.rs:302-325: the blank-altloc conformer is removed and its atoms appended to every other one.
+void reshuffle_conformers(PDB &pdb) {
+    for (Model &m : pdb.models)
+        for (Chain &c : m.chains)
+            for (Residue &r : c.residues) {
+                if (r.conformers.size() <= 1) continue;
+                int blank = -1;
+                for (size_t i = 0; i < r.conformers.size(); ++i)
+                    if (r.conformers[i].altloc.empty()) blank = (int)i;
+                if (blank < 0) continue;
+                Conformer shared = std::move(r.conformers[blank]);
+                r.conformers.erase(r.conformers.begin() + blank);
+                const double count = (double)(r.conformers.size() + 1);
+                for (Conformer &f : r.conformers)
+                    for (const AtomRec &a : shared.atoms) {
+                        AtomRec b = a;
+                        b.occupancy = a.occupancy / count;
+                        f.atoms.push_back(std::move(b));
+                    }
+            }
+}
+
+long parse_long(std::string_view s, bool *ok = nullptr) {
+    std::string t(trim(s));
+    char *end = nullptr;
+    const long v = std::strtol(t.c_str(), &end, 10);
+    if (ok) *ok = !t.empty() && end && *end == '\0';
+    return v;
+}
+
+double parse_double(std::string_view s) {
+    std::string t(trim(s));
+    return std::strtod(t.c_str(), nullptr);
+}
+
+void flush_model(PDB &pdb, Model &model) {
+    if (!model.chains.empty()) pdb.models.push_back(std::move(model));
+}
+
+}  // namespace
+
+PDB read_pdb(const std::string &path) {
+    std::ifstream fh(path);
+    if (!fh) throw std::runtime_error("cannot open " + path);
+    PDB pdb;
+    Model model;
+    long serial_add = 0, res_add = 0, last_serial = -1, last_res = -1;
+    std::string line;
+    while (std::getline(fh, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        const bool is_atom = line.compare(0, 6, "ATOM  ") == 0, is_het = line.compare(0, 6, "HETATM") == 0;
+        if (is_atom || is_het) {
+            if (line.size() < 80) line.resize(80, ' ');
+            bool ok = false;
+            long serial = parse_long(std::string_view(line).substr(6, 5), &ok);
+            if (!ok) serial = 0;
+            const std::string name = upper(trim(std::string_view(line).substr(12, 4)));
+            const char alt = line[16];
+            const std::string resname = upper(trim(std::string_view(line).substr(17, 3)));
+            const char chain_c = line[21];
+            const long resseq = parse_long(std::string_view(line).substr(22, 4));
+            const char icode = line[26];
+            const std::string_view occ_s = trim(std::string_view(line).substr(54, 6));
+            if (serial == 0 && last_serial == 99999) serial_add += 100000;
+            if (resseq == 0 && last_res == 9999) res_add += 10000;
+            AtomRec a;
+            a.hetero = is_het;
+            a.serial = (std::size_t)(serial + serial_add);
+            a.name = name;
+            a.x = parse_double(std::string_view(line).substr(30, 8));
+            a.y = parse_double(std::string_view(line).substr(38, 8));
+            a.z = parse_double(std::string_view(line).substr(46, 8));
+            a.occupancy = occ_s.empty() ? 1.0 : parse_double(occ_s);
+            a.element = resolve_element(std::string_view(line).substr(76, 2), name);
+            add_atom(model, chain_c == ' ' ? std::string("A") : std::string(1, chain_c), resseq + res_add,
+                     icode == ' ' ? std::string() : std::string(1, icode), resname, alt == ' ' ? std::string() : std::string(1, alt),
+                     std::move(a));
+            last_serial = serial;
+            last_res = resseq;
+        } else if (line.compare(0, 6, "MODEL ") == 0) {
+            flush_model(pdb, model);
+            bool ok = false;
+            const long no = parse_long(std::string_view(line).substr(6), &ok);
+            model = Model();
+            model.serial = ok ? no : (long)pdb.models.size() + 1;
+        } else if (line.compare(0, 6, "ENDMDL") == 0) {
+            const std::ptrdiff_t next = model.serial + 1;
+            flush_model(pdb, model);
+            model = Model();
+            model.serial = next;
+        }
+    }
+    flush_model(pdb, model);
+    reshuffle_conformers(pdb);
+    return pdb;
+}
+
+namespace {
+
+// One mmCIF data line -> tokens; quotes group, a quote only closes before whitespace or end of line.
+std::vector<std::string> cif_tokens(const std::string &line) {
+    std::vector<std::string> out;
+    size_t i = 0;
+    const size_t n = line.size();
+    while (i < n) {
+        while (i < n && std::isspace((unsigned char)line[i])) ++i;
+        if (i >= n) break;
+        if (line[i] == '\'' || line[i] == '"') {
+            const char q = line[i];
+            size_t j = i + 1;
+            while (j < n && !(line[j] == q && (j + 1 == n || std::isspace((unsigned char)line[j + 1])))) ++j;
+            out.emplace_back(line, i + 1, j - i - 1);
+            i = j + 1;
+        } else {
+            size_t j = i;
+            while (j < n && !std::isspace((unsigned char)line[j])) ++j;
+            out.emplace_back(line, i, j - i);
+            i = j;
+        }
+    }
+    return out;
+}
+
+}  // namespace
+
+PDB read_mmcif(const std::string &path) {
+    std::ifstream fh(path);
+    if (!fh) throw std::runtime_error("cannot open " + path);
+    PDB pdb;
+    std::unordered_map<long, size_t> model_index;
+    std::string line;
+    std::vector<std::string> lines;
+    while (std::getline(fh, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        lines.push_back(line);
+    }
+    size_t i = 0;
+    const size_t n = lines.size();
+    auto stripped = [&](size_t k) { return std::string(trim(lines[k])); };
+    while (i < n) {
+        if (stripped(i) == "loop_" && i + 1 < n && stripped(i + 1).rfind("_atom_site.", 0) == 0) {
+            ++i;
+            std::unordered_map<std::string, int> col;
+            int ncol = 0;
+            while (i < n && stripped(i).rfind("_atom_site.", 0) == 0) {
+                col[stripped(i).substr(11)] = ncol++;
+                ++i;
+            }
+            auto get = [&](const std::vector<std::string> &tok, const char *key) -> const std::string * {
+                auto it = col.find(key);
+                if (it == col.end()) return nullptr;
+                const std::string &v = tok[it->second];
+                return (v == "." || v == "?") ? nullptr : &v;
+            };
+            while (i < n) {
+                const std::string s = stripped(i);
+                if (s.empty() || s[0] == '#' || s[0] == '_' || s == "loop_") break;
+                const std::vector<std::string> tok = cif_tokens(s);
+                ++i;
+                if ((int)tok.size() < ncol) continue;
+                const std::string *v;
+                const long model_no = (v = get(tok, "pdbx_PDB_model_num")) ? parse_long(*v) : 1;
+                auto mi = model_index.find(model_no);
+                if (mi == model_index.end()) {
+                    mi = model_index.emplace(model_no, pdb.models.size()).first;
+                    pdb.models.emplace_back();
+                    pdb.models.back().serial = model_no;
+                }
+                Model &model = pdb.models[mi->second];
+                const std::string group = (v = get(tok, "group_PDB")) ? *v : "ATOM";
+                const std::string name = (v = get(tok, "label_atom_id")) ? upper(*v) : "";
+                const std::string resname = (v = get(tok, "label_comp_id")) ? upper(*v) : "";
+                const std::string *seq = get(tok, "auth_seq_id");
+                if (!seq) seq = get(tok, "label_seq_id");
+                const std::string *chain = get(tok, "auth_asym_id");
+                if (!chain) chain = get(tok, "label_asym_id");
+                AtomRec a;
+                a.hetero = group == "HETATM";
+                a.serial = model.atom_count;
+                a.name = name;
+                a.x = (v = get(tok, "Cartn_x")) ? parse_double(*v) : 0.0;
+                a.y = (v = get(tok, "Cartn_y")) ? parse_double(*v) : 0.0;
+                a.z = (v = get(tok, "Cartn_z")) ? parse_double(*v) : 0.0;
+                a.occupancy = (v = get(tok, "occupancy")) ? parse_double(*v) : 1.0;
+                a.element = resolve_element((v = get(tok, "type_symbol")) ? *v : "", name);
+                const std::string *icode = get(tok, "pdbx_PDB_ins_code"), *alt = get(tok, "label_alt_id");
+                add_atom(model, chain ? *chain : std::string(), seq ? parse_long(*seq) : 0, icode ? *icode : std::string(), resname,
+                         alt ? *alt : std::string(), std::move(a));
+            }
+            continue;
+        }
+        ++i;
+    }
+    reshuffle_conformers(pdb);
+    return pdb;
+}
+
+PDB open(const std::string &path) {
+    const size_t dot = path.find_last_of('.');
+    std::string ext = dot == std::string::npos ? "" : path.substr(dot);
+    for (char &c : ext) c = (char)std::tolower((unsigned char)c);
+    if (ext == ".cif" || ext == ".mmcif") return read_mmcif(path);
+    return read_pdb(path);
+}
+
+}  // namespace pdb
+}  // namespace rust_sasa

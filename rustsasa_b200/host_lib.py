@@ -1,0 +1,96 @@
+"""ctypes access to the C++ host layer (libsasa_b200_host.so, include/sasa_b200.hpp) for tests and tools."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsasa_b200_host.so")
+CLI_PATH = os.path.join(HERE, "sasa_b200_cli")
+LEVELS = {"atom": 0, "residue": 1, "chain": 2, "protein": 3}
+
+_lib = None
+
+
+class HostError(RuntimeError):
+    """kind = SASACalcError variant name, or "IO"."""
+
+    def __init__(self, text: str):
+        super().__init__(text)
+        self.kind = text.split(":", 1)[0]
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m rustsasa_b200.build`")
+        L = C.CDLL(LIB_PATH)
+        vp, sz = C.c_void_p, C.c_size_t
+        L.sasa_b200_host_pack.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, sz]
+        L.sasa_b200_host_pack.restype = vp
+        L.sasa_b200_host_pack_atoms.argtypes = [vp]
+        L.sasa_b200_host_pack_atoms.restype = sz
+        L.sasa_b200_host_pack_segments.argtypes = [vp]
+        L.sasa_b200_host_pack_segments.restype = sz
+        L.sasa_b200_host_pack_copy.argtypes = [vp, vp, vp, vp, vp]
+        L.sasa_b200_host_pack_copy.restype = None
+        L.sasa_b200_host_pack_free.argtypes = [vp]
+        L.sasa_b200_host_pack_free.restype = None
+        L.sasa_b200_host_process_json.argtypes = [C.c_char_p, C.c_int, C.c_float, sz, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  C.c_char_p, C.c_char_p, sz, C.c_char_p, sz]
+        L.sasa_b200_host_process_json.restype = C.c_long
+        L.sasa_b200_host_format.argtypes = [C.c_int, C.c_int, vp, sz, C.c_char_p, sz]
+        L.sasa_b200_host_format.restype = C.c_long
+        L.sasa_b200_host_serialize_chain_id.argtypes = [C.c_char_p]
+        L.sasa_b200_host_serialize_chain_id.restype = C.c_long
+        L.sasa_b200_host_get_radius.argtypes = [C.c_char_p, C.c_char_p]
+        L.sasa_b200_host_get_radius.restype = C.c_float
+        _lib = L
+    return _lib
+
+
+def pack(path: str, level: str = "residue", include_hydrogens=False, include_hetatms=False, allow_vdw_fallback=False,
+         read_radii_from_occupancy=False, radii_file: Optional[str] = None):
+    """C++ build_atoms_and_mapping on a file -> dict(xyzr, ids, seg_be, seg_polar)."""
+    L = load()
+    err = C.create_string_buffer(512)
+    h = L.sasa_b200_host_pack(path.encode(), LEVELS[level], include_hydrogens, include_hetatms, allow_vdw_fallback,
+                              read_radii_from_occupancy, radii_file.encode() if radii_file else None, err, 512)
+    if not h:
+        raise HostError(err.value.decode())
+    try:
+        n, g = L.sasa_b200_host_pack_atoms(h), L.sasa_b200_host_pack_segments(h)
+        xyzr = np.zeros((n, 4), np.float32)
+        ids = np.zeros(n, np.uint64)
+        seg = np.zeros((g, 2), np.uint32)
+        pol = np.zeros(g, np.uint8)
+        L.sasa_b200_host_pack_copy(h, xyzr.ctypes.data, ids.ctypes.data, seg.ctypes.data, pol.ctypes.data)
+    finally:
+        L.sasa_b200_host_pack_free(h)
+    return dict(xyzr=xyzr, ids=ids, seg_be=seg, seg_polar=pol)
+
+
+def process_json(path: str, level: str = "residue", probe_radius=1.4, n_points=100, include_hydrogens=False,
+                 include_hetatms=False, allow_vdw_fallback=False, read_radii_from_occupancy=False,
+                 radii_file: Optional[str] = None) -> str:
+    """SASAOptions<level>::process through the C++ layer and the GPU -> serde-style JSON text."""
+    L = load()
+    out = C.create_string_buffer(64 << 20)
+    err = C.create_string_buffer(512)
+    n = L.sasa_b200_host_process_json(path.encode(), LEVELS[level], probe_radius, n_points, include_hydrogens, include_hetatms,
+                                      allow_vdw_fallback, read_radii_from_occupancy,
+                                      radii_file.encode() if radii_file else None, out, len(out), err, 512)
+    if n < 0:
+        raise HostError(err.value.decode())
+    return out.raw[:n].decode()
+
+
+def format_values(values, xml=False, kind="atom") -> str:
+    v = np.ascontiguousarray(values, np.float32)
+    out = C.create_string_buffer(1 << 20)
+    n = load().sasa_b200_host_format(int(xml), LEVELS[kind], v.ctypes.data, v.size, out, len(out))
+    return out.raw[:n].decode()

@@ -1,0 +1,103 @@
+"""C++ host layer end to end on the GPU: SASAOptions<Level>::process and the batched directory-mode CLI
+(src/main.rs:342-480) against the Python mirror, which the parity tests pin to the oracle."""
+import json
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(ROOT, "tests", "data")
+FILES = ["mini_altloc.pdb", "mini_models.pdb", "mini.cif"]
+
+
+@pytest.fixture(scope="module")
+def host():
+    from rustsasa_b200 import build, host_lib
+    build.build_host()
+    host_lib.load()
+    return host_lib
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rustsasa_b200 import Engine
+    e = Engine()
+    yield e
+    e.close()
+
+
+def py_result(eng, path, level, **kw):
+    from rustsasa_b200 import AtomLevel, ChainLevel, ProteinLevel, ResidueLevel, SASAOptions, read_structure
+    L = dict(atom=AtomLevel, residue=ResidueLevel, chain=ChainLevel, protein=ProteinLevel)[level]
+    o = SASAOptions(L).with_n_points(kw.get("n_points", 100)).with_probe_radius(kw.get("probe_radius", 1.4))
+    return o.process(read_structure(path), eng)
+
+
+def assert_json_equals(js, res, level):
+    d = json.loads(js)
+    if level == "atom":
+        assert np.array_equal(np.array(d["Atom"], np.float32), res)
+    elif level == "residue":
+        assert [(r["serial_number"], r["insertion_code"], r["name"], r["is_polar"], r["chain_id"]) for r in d["Residue"]] == \
+               [(r.serial_number, r.insertion_code, r.name, r.is_polar, r.chain_id) for r in res]
+        assert np.array_equal(np.array([r["value"] for r in d["Residue"]], np.float32),
+                              np.array([r.value for r in res], np.float32))
+    elif level == "chain":
+        assert [c["name"] for c in d["Chain"]] == [c.name for c in res]
+        assert np.array_equal(np.array([c["value"] for c in d["Chain"]], np.float32), np.array([c.value for c in res], np.float32))
+    else:
+        p = d["Protein"]
+        assert np.array_equal(np.array([p["global_total"], p["polar_total"], p["non_polar_total"]], np.float32),
+                              np.array([res.global_total, res.polar_total, res.non_polar_total], np.float32))
+
+
+@pytest.mark.parametrize("name", FILES)
+@pytest.mark.parametrize("level", ["atom", "residue", "chain", "protein"])
+def test_process_matches_python_mirror(host, eng, name, level):
+    path = os.path.join(DATA, name)
+    assert_json_equals(host.process_json(path, level), py_result(eng, path, level), level)
+    assert_json_equals(host.process_json(path, level, probe_radius=1.0, n_points=960),
+                       py_result(eng, path, level, probe_radius=1.0, n_points=960), level)
+
+
+def test_process_errors_are_the_reference_variants(host):
+    with pytest.raises(host.HostError) as ei:
+        host.process_json(os.path.join(DATA, "mini_altloc.pdb"), "residue", include_hetatms=True)
+    assert ei.value.kind == "RadiusMissing"
+    assert json.loads(host.process_json(os.path.join(DATA, "mini_altloc.pdb"), "atom", include_hetatms=True,
+                                        allow_vdw_fallback=True))["Atom"].__len__() == 22
+
+
+def test_cli_directory_mode_is_one_batched_pipeline(host, eng, tmp_path):
+    """{stem}.{ext} naming, per-file errors collected, exit code 0 (src/main.rs:414-416, :447-479)."""
+    ind, outd = tmp_path / "in", tmp_path / "out"
+    ind.mkdir()
+    for f in FILES:
+        shutil.copy(os.path.join(DATA, f), ind / f)
+    (ind / "broken.pdb").write_text("ATOM      1  XX  UNK A   1       0.000   0.000   0.000  1.00  0.00           C\n")
+    for level in ("residue", "protein"):
+        r = subprocess.run([host.CLI_PATH, str(ind), str(outd), "--format", "json", "-o", level], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "Total errors: 1" in r.stderr and "broken" in r.stderr and "Radius not found" in r.stderr
+        assert sorted(os.listdir(outd)) == ["mini.json", "mini_altloc.json", "mini_models.json"]
+        for f in FILES:
+            js = (outd / (os.path.splitext(f)[0] + ".json")).read_text()
+            assert_json_equals(js, py_result(eng, os.path.join(DATA, f), level), level)
+        shutil.rmtree(outd)
+    r = subprocess.run([host.CLI_PATH, str(ind), str(outd), "-f", "xml", "-o", "chain", "--tile", "2"], capture_output=True, text=True)
+    assert r.returncode == 0 and (outd / "mini.xml").read_text().startswith("<Chain><name>A</name><value>")
+
+
+def test_cli_single_file_mode(host, eng, tmp_path):
+    out = tmp_path / "o.json"
+    r = subprocess.run([host.CLI_PATH, os.path.join(DATA, "mini.cif"), str(out), "-o", "atom", "-n", "200", "-p", "1.2"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert_json_equals(out.read_text(), py_result(eng, os.path.join(DATA, "mini.cif"), "atom", n_points=200, probe_radius=1.2), "atom")
+    r = subprocess.run([host.CLI_PATH, os.path.join(DATA, "mini.cif"), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode != 0                                     # output path is a directory / no format
