@@ -17,7 +17,9 @@
  *
  * Conventions
  *   - plain pointers and sizes only; no CUDA or torch types appear in any signature
- *     (streams are passed as void* holding a cudaStream_t, NULL = the context's own);
+ *     (streams are passed as void* holding a cudaStream_t -- including the special handles cudaStreamLegacy (0x1)
+ *     and cudaStreamPerThread (0x2) -- and NULL = the context's own non-blocking stream, which is NOT ordered with
+ *     the caller's default stream: synchronise with sasa_b200_batch_sync);
  *   - every call returns a sasa_b200_status; sasa_b200_last_error() gives the text;
  *     nothing in the library aborts the process and there is NO CPU fallback: if no
  *     CUDA device is present sasa_b200_create() fails with SASA_B200_ERR_CUDA;

@@ -231,7 +231,11 @@ int arena_reserve(sasa_b200_ctx *ctx, size_t bytes) {
 void build_plan(sasa_b200_batch *b, int variant) {
     sasa_b200_ctx *ctx = b->ctx;
     const bool has_cls = (variant & 1) == 1;
-    const size_t chunk_atoms = (variant & 2) ? ~(size_t)0 : kChunkAtoms;
+    static const size_t chunk_env = [] {
+        const char *e = getenv("SASA_B200_CHUNK_ATOMS");   // tuning aid: atoms per pipelined chunk of the host entry points
+        return e ? (size_t)atoll(e) : kChunkAtoms;
+    }();
+    const size_t chunk_atoms = (variant & 2) ? ~(size_t)0 : chunk_env;
     std::vector<uint32_t> cap;
     for (const SmallCfg &c : ctx->cfgs) cap.push_back(cfg_capacity(ctx, c, has_cls));
     std::vector<Chunk> &plan = b->plan[variant];

@@ -149,20 +149,26 @@ template <bool TAIL>
 __device__ __forceinline__ int tight_tile(const float4 *ent, int q0, int k, const float4 pt, int sh, int ns) {
     const int lane = lane_id();
     const int kstep = 32 >> sh;
-    int q = q0 + (lane >> sh);
+    const float4 *ep = ent + q0 + (lane >> sh);
+    const float4 *const eend = ent + k;
     const int full = (k - q0) >> (5 - sh);
-    bool hit = false;
+    // A point is occluded iff some entry has dot < limit (tail: dot <= limit), i.e. iff the largest margin
+    // limit - dot is > 0 (tail: >= 0): with gradual underflow (nvcc's default, -ftz=false) an IEEE subtraction of two
+    // floats is zero exactly when they are equal, so the sign of the rounded margin is the exact comparison.  The
+    // running FMNMX keeps the loop free of predicates and loop-carried branches (NaN margins are ignored by fmaxf,
+    // matching a false comparison).
+    float best = -INFINITY;
 #pragma unroll 2
-    for (int t = 0; t < full; ++t, q += kstep) {
-        const float4 e = ent[q];
-        if (TAIL) hit = hit | (dot_tail(pt.x, pt.y, pt.z, e) <= e.w);
-        else hit = hit | (dot_body(pt.x, pt.y, pt.z, e) < e.w);
+    for (int t = 0; t < full; ++t) {
+        const float4 e = *ep;
+        ep += kstep;
+        best = fmaxf(best, __fsub_rn(e.w, TAIL ? dot_tail(pt.x, pt.y, pt.z, e) : dot_body(pt.x, pt.y, pt.z, e)));
     }
-    if (q < k) {
-        const float4 e = ent[q];
-        if (TAIL) hit = hit | (dot_tail(pt.x, pt.y, pt.z, e) <= e.w);
-        else hit = hit | (dot_body(pt.x, pt.y, pt.z, e) < e.w);
+    if (ep < eend) {
+        const float4 e = *ep;
+        best = fmaxf(best, __fsub_rn(e.w, TAIL ? dot_tail(pt.x, pt.y, pt.z, e) : dot_body(pt.x, pt.y, pt.z, e)));
     }
+    const bool hit = TAIL ? (best >= 0.0f) : (best > 0.0f);
     // OR over the lanes that share a point: one REDUX.OR of per-point bits
     const unsigned hm = __reduce_or_sync(kFull, hit ? (1u << (lane & ((1 << sh) - 1))) : 0u);
     const unsigned valid = ns >= 32 ? 0xffffffffu : ((1u << ns) - 1u);

@@ -44,6 +44,17 @@ def _ptr(a) -> Optional[int]:
     return int(a.data_ptr())   # torch tensor
 
 
+def _stream(stream) -> int:
+    """cudaStream_t handle for the device entry points.  None = torch's CURRENT stream, so that work enqueued here
+    is ordered with the caller's other torch / NCCL work (the legacy default stream is passed as cudaStreamLegacy = 1,
+    because NULL means "the context's own stream" in the C ABI); an int is passed through as a raw handle."""
+    if stream is None:
+        import torch
+        h = int(torch.cuda.current_stream().cuda_stream)
+        return h if h != 0 else 1
+    return int(stream)
+
+
 def _np(a, dtype, shape=None):
     if a is None:
         return None
@@ -200,21 +211,22 @@ class Batch:
         return res
 
     def run_device(self, d_xyzr, d_id_class=None, probe_radius=1.4, n_points=100, simd_lanes=8, flags=0,
-                   counts=None, atom_sasa=None, seg_sasa=None, protein=None, stream: int = 0):
-        """All tensors are torch CUDA tensors; enqueues on `stream` (a raw cudaStream_t, 0 = context stream)."""
+                   counts=None, atom_sasa=None, seg_sasa=None, protein=None, stream=None):
+        """All tensors are torch CUDA tensors; enqueues on `stream` (None = torch's current stream, else a raw
+        cudaStream_t handle) and returns without synchronising."""
         outs = _lib.Outputs(_ptr(counts), _ptr(atom_sasa), _ptr(seg_sasa), _ptr(protein))
         prm = self._params(probe_radius, n_points, simd_lanes, flags)
         self.engine._check(self._L.sasa_b200_batch_run_device(self._h, _ptr(d_xyzr), _ptr(d_id_class), C.byref(prm),
-                                                             C.byref(outs), stream or None))
+                                                             C.byref(outs), _stream(stream)))
 
     def run_atom_range_device(self, d_xyzr, rank: int, n_ranks: int, d_id_class=None, probe_radius=1.4, n_points=100,
-                              simd_lanes=8, counts=None, atom_sasa=None, stream: int = 0):
+                              simd_lanes=8, counts=None, atom_sasa=None, stream=None):
         """Atom-range split (cfg5): slice `rank` of `n_ranks` of every structure's cell-sorted atom order; the
         output tensors are zero outside the slice, ready for an all-reduce(SUM) across ranks."""
         prm = self._params(probe_radius, n_points, simd_lanes, 0)
         self.engine._check(self._L.sasa_b200_batch_run_atom_range_device(
             self._h, _ptr(d_xyzr), _ptr(d_id_class), C.byref(prm), rank, n_ranks, _ptr(counts), _ptr(atom_sasa),
-            stream or None))
+            _stream(stream)))
 
     def run_atom_range_host(self, xyzr, rank: int, n_ranks: int, id_class=None, probe_radius=1.4, n_points=100,
                             simd_lanes=8) -> BatchResult:
@@ -230,10 +242,10 @@ class Batch:
         res.stats = st.as_dict()
         return res
 
-    def reduce_device(self, d_atom_sasa, seg_sasa=None, protein=None, stream: int = 0):
+    def reduce_device(self, d_atom_sasa, seg_sasa=None, protein=None, stream=None):
         """Level sums of a finished per-atom SASA vector (torch CUDA tensors)."""
         self.engine._check(self._L.sasa_b200_batch_reduce_device(self._h, _ptr(d_atom_sasa), _ptr(seg_sasa), _ptr(protein),
-                                                                stream or None))
+                                                                _stream(stream)))
 
     def sync(self) -> dict:
         st = _lib.Stats()

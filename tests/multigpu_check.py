@@ -47,16 +47,15 @@ def main():
     a = W.capsid_shell(120000)
     b = eng.batch(a.struct_off, a.seg_be, a.struct_seg_off, a.seg_polar)
     d_xyzr = torch.from_numpy(a.xyzr).cuda()
-    stream = torch.cuda.current_stream().cuda_stream
 
     def compute_range(r, w):
         counts = torch.empty(a.n_atoms, dtype=torch.int32, device="cuda")
         atom = torch.empty(a.n_atoms, dtype=torch.float32, device="cuda")
-        b.run_atom_range_device(d_xyzr, r, w, n_points=960, counts=counts, atom_sasa=atom, stream=stream)
+        b.run_atom_range_device(d_xyzr, r, w, n_points=960, counts=counts, atom_sasa=atom)
         return counts, atom
     counts, atom = run_atom_range(compute_range)
     d_seg = torch.zeros(len(a.seg_be), dtype=torch.float32, device="cuda")
-    b.reduce_device(atom, d_seg, None, stream=stream)
+    b.reduce_device(atom, d_seg, None)
     torch.cuda.synchronize()
     b.sync()
     single = b.run_host(a.xyzr, n_points=960, want=("counts", "atom", "seg"))
