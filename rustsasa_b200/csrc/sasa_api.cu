@@ -249,6 +249,22 @@ void build_plan(sasa_b200_batch *b, int variant) {
         ch.s0 = s;
         ch.a0 = b->h_off[s];
         while (s < b->S && (b->h_off[s] - ch.a0 < chunk_atoms || s == ch.s0)) ++s;
+        // equal-sized structures (MD frames) finish in lock step: cut the chunk at a whole number of waves of the
+        // widest configuration so that no launch ends with a mostly idle last round
+        if (s < b->S && chunk_atoms != ~(size_t)0) {
+            const uint32_t n0 = b->h_off[ch.s0 + 1] - b->h_off[ch.s0];
+            bool uniform = true;
+            for (uint32_t i = ch.s0; i < s && uniform; ++i) uniform = (b->h_off[i + 1] - b->h_off[i]) == n0;
+            if (uniform) {
+                size_t k = 0;
+                while (k < cap.size() && n0 > cap[k]) ++k;
+                if (k < cap.size()) {
+                    const uint32_t slots = (uint32_t)(ctx->sm_count * ctx->cfgs[k].minb);
+                    uint32_t want = ((s - ch.s0 + slots - 1) / slots) * slots;
+                    while (s < b->S && s - ch.s0 < want && b->h_off[s + 1] - b->h_off[s] == n0) ++s;
+                }
+            }
+        }
         ch.s1 = s;
         ch.a1 = b->h_off[s];
         ch.g0 = b->h_seg_off.empty() ? 0 : b->h_seg_off[ch.s0];
@@ -657,6 +673,13 @@ static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz
     KParams kbase;
     make_kparams(b, ra, &kbase);
     b->launches_last = 0;
+    // MD form: the fused kernels read the 12-byte coordinates and the shared radius table directly; only batches with
+    // structures on the large-structure path still expand to float4 first
+    const bool fused_frames = frames && b->max_large == 0;
+    if (fused_frames) {
+        kbase.xyz3 = reinterpret_cast<const float *>(base_p + o_xyz3);
+        kbase.radii = reinterpret_cast<const float *>(base_p + o_rad);
+    }
 
     cudaEvent_t ev0, ev1;
     CU_TRY(ctx, cudaEventCreate(&ev0));
@@ -676,10 +699,10 @@ static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz
         if (na) {
             if (frames) {
                 CU_TRY(ctx, cudaMemcpyAsync(base_p + o_xyz3 + ch.a0 * 12, xyz3 + ch.a0 * 3, na * 12, cudaMemcpyHostToDevice, st));
-                pack_frames_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(
+                if (!fused_frames) pack_frames_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(
                     reinterpret_cast<const float *>(base_p + o_xyz3) + ch.a0 * 3, reinterpret_cast<const float *>(base_p + o_rad),
                     reinterpret_cast<float4 *>(base_p + o_xyzr) + ch.a0, (uint32_t)na, (uint32_t)fN, (uint32_t)(ch.a0 % (fN ? fN : 1)));
-                ++b->launches_last;
+                if (!fused_frames) ++b->launches_last;
             } else {
                 CU_TRY(ctx, cudaMemcpyAsync(base_p + o_xyzr + ch.a0 * 16, xyzr + ch.a0 * 4, na * 16, cudaMemcpyHostToDevice, st));
             }

@@ -27,6 +27,7 @@ constexpr double kBoundaryTol = 1.0e-5;
 struct KParams {
     // batch (device pointers)
     const float4 *xyzr;
+    const float *xyz3, *radii;    // MD form (fused kernels only): 3 floats per atom + per-frame-index radii; else null
     const uint32_t *cls;          // nullable
     const uint32_t *struct_off;   // S+1
     const uint32_t *order;        // structures handled by this launch

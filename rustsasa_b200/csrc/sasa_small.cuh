@@ -77,6 +77,16 @@ __device__ __forceinline__ void block_minmax8(float (&v)[8], float *red) {
     __syncthreads();
 }
 
+// Atom i of the structure that starts at a0: packed float4, or -- MD-trajectory form -- 12-byte coordinates plus the
+// radius table shared by all frames (what sasa_b200_batch_run_frames_host uploads; no intermediate float4 copy).
+__device__ __forceinline__ float4 load_atom(const KParams &p, uint32_t a0, int i) {
+    if (p.xyz3) {
+        const float *q = p.xyz3 + 3 * ((size_t)a0 + (size_t)i);
+        return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(p.radii + i));
+    }
+    return __ldg(p.xyzr + a0 + i);
+}
+
 // Views of the dynamic shared memory of one CTA (see small_layout).
 struct SmemView {
     float4 *ptab;       // 128 sphere points as float4 (n_points <= 128), else unused
@@ -127,11 +137,10 @@ template <int NT, bool HAS_CLS>
 __device__ __forceinline__ bool structure_setup(const KParams &p, const SmemView &V, uint32_t sid, uint32_t a0, int N,
                                                 Grid &g, int &ncell) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float4 *gat = p.xyzr + a0;
     // ---- bounds, r_max, finiteness (maxima of {-min, max, r, bad}) -------------------------------------
     float red8[8] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0f, 0.0f};
     for (int i = tid; i < N; i += NT) {
-        const float4 a = __ldg(gat + i);
+        const float4 a = load_atom(p, a0, i);
         const bool fin = isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(a.w);
         red8[0] = fmaxf(red8[0], -a.x); red8[1] = fmaxf(red8[1], -a.y); red8[2] = fmaxf(red8[2], -a.z);
         red8[3] = fmaxf(red8[3], a.x);  red8[4] = fmaxf(red8[4], a.y);  red8[5] = fmaxf(red8[5], a.z);
@@ -176,7 +185,7 @@ __device__ __forceinline__ bool structure_setup(const KParams &p, const SmemView
     for (int i = tid; i < (ncell + 2 + 1) / 2; i += NT) V.cellw[i] = 0u;
     __syncthreads();
     for (int i = tid; i < N; i += NT) {
-        const float4 a = __ldg(gat + i);
+        const float4 a = load_atom(p, a0, i);
         const int c = (cell_coord(a.z, g.minz, g.inv_c, g.nz) * g.ny + cell_coord(a.y, g.miny, g.inv_c, g.ny)) * g.nx +
                       cell_coord(a.x, g.minx, g.inv_c, g.nx);
         const uint32_t old = atomicAdd(&V.cellw[c >> 1], (c & 1) ? 0x10000u : 1u);
@@ -211,7 +220,7 @@ __device__ __forceinline__ bool structure_setup(const KParams &p, const SmemView
     }
     for (int i = tid; i < N; i += NT) {
         const int at = (int)V.cell[V.cellid[i]] + (int)V.rank[i];
-        V.atom[at] = __ldg(gat + i);
+        V.atom[at] = load_atom(p, a0, i);
         V.orig[at] = (uint16_t)i;
         if (HAS_CLS) V.cls[at] = p.cls[a0 + i];
     }
@@ -228,10 +237,9 @@ __device__ __forceinline__ bool structure_setup(const KParams &p, const SmemView
 template <int NT>
 __device__ __forceinline__ void structure_outputs(const KParams &p, const SmemView &V, uint32_t sid, uint32_t a0, int N) {
     const int tid = threadIdx.x;
-    const float4 *gat = p.xyzr + a0;
     for (int i = tid; i < N; i += NT) {
         const float cnt = V.val[i];
-        const float area = atom_area(__ldg(gat + i).w, p.probe, cnt, p.inv_n);
+        const float area = atom_area(p.xyz3 ? __ldg(p.radii + i) : __ldg(p.xyzr + a0 + i).w, p.probe, cnt, p.inv_n);
         if (p.out_counts) p.out_counts[a0 + i] = (uint32_t)cnt;
         if (p.out_atom) p.out_atom[a0 + i] = area;
         V.val[i] = area;
