@@ -105,6 +105,19 @@ def peaks():
     return p
 
 
+def ncu_traffic(n_structures):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this same command
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); None when the workload differs."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            t = json.load(fh)
+        if int(t.get("structures", -1)) != int(n_structures):
+            return None, None
+        return float(t["dram_bytes_per_step"]), t
+    except Exception:
+        return None, None
+
+
 def cpu_sample(data, seconds_target=15.0, threads=0):
     """Time the oracle's -O3 build (C restatement of RustSASA's CPU path, directory-mode threading: one structure
     per task over all host cores) on a bounded prefix of the batch.  Returns (atoms/s, info)."""
@@ -310,11 +323,15 @@ def main():
         k_mean = cpu["k_mean"] if cpu else 43.1
         flops_per_atom = FLOP_PER_TEST * N_POINTS * k_mean + FLOP_PER_PAIR * k_mean
         per_gpu_step_s = dev_ms_max * 1e-3 / args.steps
+        traffic, traffic_info = ncu_traffic(args.structures)
         achieved = N * flops_per_atom / per_gpu_step_s / 1e12
         out["roofline"] = {
             "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-            "traffic": None,
-            "kernel": "sasa_small_kernel (fused per-structure kernel; all launches of a step)",
+            "traffic": traffic,
+            "traffic_unit": "DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum over the step's launches)",
+            "traffic_source": (traffic_info or {}).get("source"),
+            "algorithmic_bytes_per_step": N * BYTES_PER_ATOM,
+            "kernel": "sasa_tight_kernel (fused per-structure kernel; all launches of a step)",
             "note": ("FP32 CUDA-core compare roofline (SURVEY.md 8d): algorithmic flops = atoms x (6 x n_points + 20) x k_mean, "
                      f"k_mean = {k_mean:.2f} reference-definition neighbours/atom measured by the oracle on a sample; "
                      f"peak = SMs x 128 x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']}); early exit may legitimately push frac past "

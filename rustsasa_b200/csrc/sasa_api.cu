@@ -55,6 +55,11 @@ struct sasa_b200_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t streams[kStreams] = {};
+    // fork/join helpers: the launches of one chunk (one per shared-memory bucket) run on sibling streams so that the
+    // tail of one kernel is back-filled by the CTAs of the next instead of idling the SMs
+    static constexpr int kSide = 3;
+    cudaStream_t side[kSide] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
     std::map<uint32_t, Points> points;
     int *d_err = nullptr;
     unsigned long long *d_stat = nullptr;
@@ -358,10 +363,17 @@ int check_params(sasa_b200_ctx *ctx, const sasa_b200_params *p) {
     return SASA_B200_OK;
 }
 
-// Enqueue every kernel of one chunk on `st`.
+// Enqueue every kernel of one chunk: the first fused launch on `st`, the others on sibling streams forked from and
+// joined back into `st` (so the caller still sees one stream-ordered unit of work).  Large-structure pipelines stay
+// on `st`.
 int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParams &base, cudaStream_t st,
                   uint32_t *launches) {
     sasa_b200_ctx *ctx = b->ctx;
+    int n_small = 0;
+    for (const Launch &L : ch.launches) n_small += L.cfg >= 0;
+    const bool fork = n_small > 1 && n_small <= sasa_b200_ctx::kSide + 1;
+    if (fork) CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
+    int small_idx = 0, forked = 0;
     for (const Launch &L : ch.launches) {
         KParams kp = base;
         kp.order = b->d_order[variant] + L.order_off;
@@ -379,11 +391,22 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
         kp.cmax = c.cmax;
         const size_t smem = small_layout(kp.nmax, kp.cmax, c.nt / 32, has_cls).total;
         const int grid = (int)std::min<uint32_t>(L.n_work, (uint32_t)(ctx->sm_count * c.minb));
+        cudaStream_t ls = st;
+        if (fork && small_idx > 0) {
+            ls = ctx->side[small_idx - 1];
+            CU_TRY(ctx, cudaStreamWaitEvent(ls, ctx->ev_fork, 0));
+        }
         void *args[] = {(void *)&kp};
-        cudaError_t e = cudaLaunchKernel((const void *)kProtos[c.proto].fn[(has_cls ? 1 : 0) + ((kp.n_points <= 128 && (kp.flags & 3u) == 0) ? 2 : 0)], dim3(grid), dim3(c.nt), args, smem, st);
+        cudaError_t e = cudaLaunchKernel((const void *)kProtos[c.proto].fn[(has_cls ? 1 : 0) + ((kp.n_points <= 128 && (kp.flags & 3u) == 0) ? 2 : 0)], dim3(grid), dim3(c.nt), args, smem, ls);
         if (e != cudaSuccess) return fail(ctx, SASA_B200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+        if (ls != st) {
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_join[small_idx - 1], ls));
+            forked = small_idx;
+        }
+        ++small_idx;
         ++*launches;
     }
+    for (int i = 0; i < forked; ++i) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
     return SASA_B200_OK;
 }
 
@@ -448,6 +471,11 @@ int sasa_b200_create(int device, sasa_b200_ctx **out_ctx) {
     for (int i = 0; i < kStreams; ++i)
         if ((e = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking)) != cudaSuccess)
             return bail(SASA_B200_ERR_CUDA, "cudaStreamCreate", e);
+    for (int i = 0; i < sasa_b200_ctx::kSide; ++i) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaStreamCreate", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaEventCreate", e);
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaEventCreate", e);
     if ((e = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(SASA_B200_ERR_OUT_OF_MEMORY, "cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_stat, 3 * sizeof(unsigned long long))) != cudaSuccess) return bail(SASA_B200_ERR_OUT_OF_MEMORY, "cudaMalloc", e);
     cudaMemset(ctx->d_err, 0, sizeof(int));
@@ -469,6 +497,11 @@ void sasa_b200_destroy(sasa_b200_ctx *ctx) {
     for (auto &kv : ctx->points) cudaFree(kv.second.d);
     for (int i = 0; i < kStreams; ++i)
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
+    for (int i = 0; i < sasa_b200_ctx::kSide; ++i) {
+        if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     cudaFree(ctx->d_err);
     cudaFree(ctx->d_stat);
     cudaFree(ctx->arena);

@@ -14,7 +14,7 @@ nproc > $OUT/nproc.txt
 # launch list: every kernel of 1 warm-up + 2 timed steps of the device leg (cold-cache, serialised: compare shares)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/launches_bench.log 2>&1
-# full capture of the dominant kernel (a smaller batch keeps the ~40 replays short)
+# full capture of the dominant kernel on the bench workload itself (2 launches x ~40 replays)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:sasa_tight_kernel -s 2 -c 2 \
-    -o $OUT/prof python bench.py --steps 1 --warmup 3 --no-cpu --structures 1100 > $OUT/prof_bench.log 2>&1
+    -o $OUT/prof python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/prof_bench.log 2>&1
 ls -la $OUT

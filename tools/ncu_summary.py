@@ -35,7 +35,29 @@ def raw(rep):
     return rows[0], rows[1], rows[2:]
 
 
+def to_bytes(value, unit):
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    return float(value.replace(",", "")) * scale.get(unit, 1.0)
+
+
+def traffic(rep, structures, out):
+    """--traffic: profiles/ncu_traffic.json for bench.py (DRAM bytes of the captured step = sum over its launches)."""
+    import json
+    hdr, units, rows = raw(rep)
+    col = {h: i for i, h in enumerate(hdr)}
+    total, per = 0.0, []
+    for r in rows:
+        b = sum(to_bytes(r[col[k]], units[col[k]]) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        per.append({"kernel": r[col["Kernel Name"]], "grid": r[col["Grid Size"]], "dram_bytes": b})
+        total += b
+    json.dump({"structures": structures, "dram_bytes_per_step": total, "launches": per,
+               "source": f"ncu --set full --clock-control none, {rep.split('/')[-2]}/{rep.split('/')[-1]}"}, open(out, "w"), indent=1)
+    print(out, total)
+
+
 def main():
+    if sys.argv[1] == "--traffic":
+        return traffic(sys.argv[2], int(sys.argv[3]), sys.argv[4])
     rep = sys.argv[1]
     hdr, units, rows = raw(rep)
     col = {h: i for i, h in enumerate(hdr)}
