@@ -168,7 +168,8 @@ SASA_B200_API int sasa_b200_batch_run_frames_host(sasa_b200_batch *batch, const 
  * split across 8 GPUs).  The reference has no counterpart -- its neighbour build is serial and its atom loop is a
  * rayon par_iter inside one process (src/lib.rs:278-290); this is that par_iter cut across devices.  Every rank
  * holds ALL atoms of the batch, rebuilds the cell list redundantly (cheaper than exchanging it) and evaluates
- * only slice `rank` of `n_ranks` of each structure's CELL-SORTED atom order, i.e. a spatially compact slab.
+ * only slice `rank` of `n_ranks` of each structure's CELL-SORTED atom order, i.e. a spatially compact slab (cut at
+ * cell boundaries, which are identical on every rank, so the slices partition the atoms exactly).
  * counts / atom_sasa are written for the slice's atoms and ZERO elsewhere, so the element-wise sum over ranks
  * (ncclAllReduce on the device variant) equals the single-GPU result bit for bit.  Level sums are not produced
  * here: reduce the summed per-atom vector with sasa_b200_batch_reduce_device or on the host. */

@@ -46,7 +46,7 @@ struct SmallCfg {
 };
 
 constexpr int kStreams = 3;
-constexpr size_t kChunkAtoms = 1500000;
+constexpr size_t kChunkAtoms = 1000000;
 
 }  // namespace
 
@@ -253,7 +253,9 @@ void build_plan(sasa_b200_batch *b, int variant) {
         Chunk ch;
         ch.s0 = s;
         ch.a0 = b->h_off[s];
-        while (s < b->S && (b->h_off[s] - ch.a0 < chunk_atoms || s == ch.s0)) ++s;
+        // the first chunks are smaller so that the first kernel starts after a short copy (ramp 1/8, 1/4, 1/2, 1, 1, ...)
+        const size_t ramp = plan.size() < 3 && chunk_atoms != ~(size_t)0 ? chunk_atoms >> (3 - plan.size()) : chunk_atoms;
+        while (s < b->S && (b->h_off[s] - ch.a0 < ramp || s == ch.s0)) ++s;
         // equal-sized structures (MD frames) finish in lock step: cut the chunk at a whole number of waves of the
         // widest configuration so that no launch ends with a mostly idle last round
         if (s < b->S && chunk_atoms != ~(size_t)0) {
@@ -282,6 +284,23 @@ void build_plan(sasa_b200_batch *b, int variant) {
             while (k < cap.size() && n > cap[k]) ++k;
             bucket[k].push_back(i);
             if (k == cap.size()) b->max_large = std::max(b->max_large, n);
+        }
+        // One launch per chunk wherever that costs little: every extra bucket is an extra kernel with its own ramp-up
+        // and tail (measured on the proteome batch: 953 vs 875 M atoms/s end to end).  If the widest fused
+        // configuration in use holds a fifth or more of the chunk's fused atoms, the smaller buckets join it.
+        for (size_t k = cap.size(); k-- > 1;) {
+            if (bucket[k].empty()) continue;
+            uint64_t atoms_k = 0, atoms_below = 0;
+            for (uint32_t i : bucket[k]) atoms_k += b->h_off[i + 1] - b->h_off[i];
+            for (size_t j = 0; j < k; ++j)
+                for (uint32_t i : bucket[j]) atoms_below += b->h_off[i + 1] - b->h_off[i];
+            if (atoms_below && atoms_k * 5 >= atoms_k + atoms_below) {
+                for (size_t j = 0; j < k; ++j) {
+                    bucket[k].insert(bucket[k].end(), bucket[j].begin(), bucket[j].end());
+                    bucket[j].clear();
+                }
+            }
+            break;   // only the widest bucket in use absorbs
         }
         for (size_t k = 0; k < bucket.size(); ++k) {
             if (bucket[k].empty()) continue;
@@ -371,7 +390,10 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
     sasa_b200_ctx *ctx = b->ctx;
     int n_small = 0;
     for (const Launch &L : ch.launches) n_small += L.cfg >= 0;
-    const bool fork = n_small > 1 && n_small <= sasa_b200_ctx::kSide + 1;
+    static const bool no_fork = getenv("SASA_B200_NO_FORK") != nullptr;   // tuning aid
+    // device-resident runs only: in the pipelined host path the sibling streams would be shared by chunks in flight on
+    // different copy streams and delay their D2H (measured: -5 % end to end), while the next chunk back-fills anyway
+    const bool fork = !no_fork && (variant & 2) && n_small > 1 && n_small <= sasa_b200_ctx::kSide + 1;
     if (fork) CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, st));
     int small_idx = 0, forked = 0;
     for (const Launch &L : ch.launches) {

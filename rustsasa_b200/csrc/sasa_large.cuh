@@ -19,7 +19,8 @@ struct LargeHeader {
     unsigned enc[8];   // order-preserving encodings of min xyz, max xyz, rmax; [7] = non-finite flag
     Grid grid;
     int ncell;
-    unsigned next_atom;
+    unsigned next_atom;   // work counter of large_atoms_kernel: next cell-sorted position to hand out
+    unsigned range_end;   // atom-range split: end of this rank's slice (a cell boundary)
 };
 
 struct LargeWorkspace {
@@ -44,7 +45,7 @@ __device__ __forceinline__ float dec_f(unsigned u) {
 __global__ void large_init_kernel(LargeHeader *h, unsigned first_atom) {
     if (threadIdx.x < 3) h->enc[threadIdx.x] = 0xffffffffu;          // running minima
     else if (threadIdx.x < 8) h->enc[threadIdx.x] = 0u;              // running maxima, flag
-    if (threadIdx.x == 0) h->next_atom = first_atom;
+    if (threadIdx.x == 0) { h->next_atom = first_atom; h->range_end = 0u; }
 }
 
 __global__ void __launch_bounds__(256) large_bounds_kernel(const float4 *__restrict__ at, int N, LargeHeader *h) {
@@ -216,6 +217,26 @@ __global__ void __launch_bounds__(256) large_scatter_kernel(const float4 *__rest
     }
 }
 
+// Atom-range split: turn the ideal cut points N*r/n and N*(r+1)/n into CELL boundaries of the sorted order.  The
+// order of atoms inside a cell comes from atomics and differs from GPU to GPU, but the cell starts are the same
+// everywhere, so slices cut at cell boundaries partition the atoms identically on every rank.
+__global__ void large_range_kernel(LargeHeader *h, const uint32_t *cells, uint32_t target_lo, uint32_t target_hi, uint32_t N) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = h->ncell;
+    auto first_start_at_or_after = [&](uint32_t target) -> uint32_t {
+        if (target >= N || n == 0) return N;
+        int lo = 0, hi = n;            // cells[n] == N
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cells[mid] >= target) hi = mid;
+            else lo = mid + 1;
+        }
+        return cells[lo];
+    };
+    h->next_atom = first_start_at_or_after(target_lo);
+    h->range_end = first_start_at_or_after(target_hi);
+}
+
 // One warp per atom; warps pull consecutive cell-sorted atoms from a global counter (which starts at the first
 // position of this launch's range) so that the warps of a CTA share candidate cells in L1.  Only sorted positions
 // below N are evaluated: N = the structure's atom count, or the end of this rank's slice in the atom-range split.
@@ -228,6 +249,7 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
     static_assert(kNbCap * 2 >= kQueueCap, "survivor queue must fit the candidate list");
     __shared__ __align__(16) float4 s_ptab[128];
     if (h->ncell == 0) return;
+    if (N < 0) N = (int)h->range_end;   // atom-range split: the slice end was computed on the device
     const Grid g = h->grid;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     float4 *w_ent = s_ent + warp * kNbCap;
@@ -410,7 +432,7 @@ inline int large_enqueue(int sm_count, LargeWorkspace &w, const KParams &kp, con
         const int gb = std::min((N + 255) / 256, sm_count * 8);
         const int cell_blocks = (int)((w.cap_cells + kScanItems - 1) / kScanItems);
         const uint32_t lo = (uint32_t)((uint64_t)N * range_rank / range_n), hi = (uint32_t)((uint64_t)N * (range_rank + 1) / range_n);
-        large_init_kernel<<<1, 32, 0, st>>>(w.hdr, lo);
+        large_init_kernel<<<1, 32, 0, st>>>(w.hdr, 0u);
         large_bounds_kernel<<<gb, 256, 0, st>>>(at, N, w.hdr);
         large_grid_kernel<<<1, 32, 0, st>>>(w.hdr, kp.probe, w.cap_cells, kp.err_flag);
         large_zero_kernel<<<sm_count * 4, 256, 0, st>>>(w.hdr, w.cells);
@@ -419,8 +441,13 @@ inline int large_enqueue(int sm_count, LargeWorkspace &w, const KParams &kp, con
         large_scan2_kernel<<<1, 1024, 0, st>>>(w.hdr, w.blocksum);
         large_scan3_kernel<<<cell_blocks, 256, 0, st>>>(w.hdr, w.cells, w.blocksum, (uint32_t)N);
         large_scatter_kernel<<<gb, 256, 0, st>>>(at, cls, N, w.hdr, w.cells, w.cellid, w.rank, w.sorted, w.orig, w.cls_sorted);
+        if (range_n > 1) {
+            large_range_kernel<<<1, 32, 0, st>>>(w.hdr, w.cells, lo, hi, (uint32_t)N);
+            ++*launches;
+        }
         const int ga = std::max(1, std::min((int)(hi - lo + 7) / 8, sm_count * 2));
-        large_atoms_kernel<<<ga, 256, 0, st>>>(kp, (int)hi, a0, w.hdr, w.sorted, w.orig, cls ? w.cls_sorted : nullptr, w.cells, w.val);
+        large_atoms_kernel<<<ga, 256, 0, st>>>(kp, range_n > 1 ? -1 : N, a0, w.hdr, w.sorted, w.orig, cls ? w.cls_sorted : nullptr,
+                                               w.cells, w.val);
         *launches += 10;
         // level sums; also blanks the outputs of a structure with non-finite input (kp carries no segments and
         // no protein output in the atom-range split, where the per-atom values of other ranks are missing)
