@@ -40,8 +40,9 @@ struct Points {
 
 struct SmallCfg {
     int nt, minb;
-    uint32_t nmax, cmax;
-    size_t smem[2];  // dynamic shared memory limit set on the kernel: without / with id classes
+    uint32_t cap[2];   // atom capacity without / with id classes (compile-time constants of the configuration)
+    uint32_t cmax;
+    size_t smem[2];    // dynamic shared memory of a launch: without / with id classes
     int proto;
 };
 
@@ -129,20 +130,18 @@ typedef void (*SmallKernel)(const KParams);
 struct Proto {
     int nt, minb;
     uint32_t cmax;
+    uint32_t cap[2];     // max_atoms(...) without / with id classes
     SmallKernel fn[4];   // index = has_cls + 2 * tight (tight: n_points <= 128, no statistics / forced streaming)
 };
-#define SASA_PROTO(NT, MINB, CMAX)                                                                        \
-    Proto { NT, MINB, CMAX, { sasa_small_kernel<NT, MINB, false>, sasa_small_kernel<NT, MINB, true>, \
-                              sasa_tight_kernel<NT, MINB, false>, sasa_tight_kernel<NT, MINB, true> } }
+#define SASA_PROTO(NT, MINB, CMAX)                                                                                     \
+    Proto { NT, MINB, CMAX, { max_atoms(NT, MINB, CMAX, false), max_atoms(NT, MINB, CMAX, true) },                     \
+            { sasa_small_kernel<NT, MINB, false, CMAX>, sasa_small_kernel<NT, MINB, true, CMAX>,                       \
+              sasa_tight_kernel<NT, MINB, false, CMAX>, sasa_tight_kernel<NT, MINB, true, CMAX> } }
 // 0-2 keep 32 warps resident per SM (64 registers/thread); 3-4 keep 24 warps (85 registers/thread)
 const Proto kProtos[] = {SASA_PROTO(256, 4, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384),
                          SASA_PROTO(384, 2, 8192), SASA_PROTO(768, 1, 16384)};
 const char *kDefaultCfgs = "12";
 constexpr int kNumProtos = sizeof(kProtos) / sizeof(kProtos[0]);
-
-size_t cfg_budget(const sasa_b200_ctx *ctx, int minb) {
-    return std::min<size_t>(ctx->smem_optin, (228 * 1024) / minb - 1024);
-}
 
 int build_cfgs(sasa_b200_ctx *ctx) {
     const char *only = getenv("SASA_B200_CFGS");   // e.g. "34": choose the configurations (tuning aid)
@@ -150,38 +149,24 @@ int build_cfgs(sasa_b200_ctx *ctx) {
     for (int i = 0; i < kNumProtos; ++i) {
         const Proto &pr = kProtos[i];
         if (!strchr(only, '0' + i)) continue;
-        const size_t budget = cfg_budget(ctx, pr.minb);
-        SmallCfg c{pr.nt, pr.minb, 0, pr.cmax, {0, 0}, i};
-        uint32_t lo = 0, hi = 65520 / 16;   // largest nmax (multiple of 16) whose class-less layout fits
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi + 1) / 2;
-            if (small_layout(mid * 16, pr.cmax, pr.nt / 32, false).total <= budget) lo = mid;
-            else hi = mid - 1;
-        }
-        c.nmax = lo * 16;
-        if (c.nmax == 0) return fail(ctx, SASA_B200_ERR_CUDA, "device shared memory too small for the fused kernel");
-        c.smem[0] = small_layout(c.nmax, c.cmax, c.nt / 32, false).total;
-        c.smem[1] = budget;
+        SmallCfg c{pr.nt, pr.minb, {pr.cap[0], pr.cap[1]}, pr.cmax, {0, 0}, i};
+        for (int v = 0; v < 2; ++v) c.smem[v] = small_layout(c.cap[v], c.cmax, c.nt / 32, v == 1).total;
+        if (c.cap[0] == 0 || c.cap[1] == 0 || std::max(c.smem[0], c.smem[1]) > ctx->smem_optin)
+            return fail(ctx, SASA_B200_ERR_UNSUPPORTED, "the fused kernels are laid out for 228 KB of shared memory per SM (B200); this device offers %zu per block",
+                        ctx->smem_optin);
         for (int v = 0; v < 4; ++v) {
             cudaError_t e = cudaFuncSetAttribute((const void *)pr.fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem[v & 1]);
             if (e != cudaSuccess)
-                return fail(ctx, SASA_B200_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", c.smem[v], cudaGetErrorString(e));
+                return fail(ctx, SASA_B200_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", c.smem[v & 1], cudaGetErrorString(e));
         }
         ctx->cfgs.push_back(c);
     }
     if (ctx->cfgs.empty()) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "SASA_B200_CFGS selects no kernel configuration");
-    std::sort(ctx->cfgs.begin(), ctx->cfgs.end(), [](const SmallCfg &a, const SmallCfg &b) { return a.nmax < b.nmax; });
+    std::sort(ctx->cfgs.begin(), ctx->cfgs.end(), [](const SmallCfg &a, const SmallCfg &b) { return a.cap[0] < b.cap[0]; });
     return SASA_B200_OK;
 }
 
-// With id classes every atom costs 4 more bytes of shared memory: the atom capacity of a config shrinks.
-uint32_t cfg_capacity(const sasa_b200_ctx *ctx, const SmallCfg &c, bool has_cls) {
-    if (!has_cls) return c.nmax;
-    const size_t budget = cfg_budget(ctx, c.minb);
-    uint32_t n = c.nmax;
-    while (n > 0 && small_layout(n, c.cmax, c.nt / 32, true).total > budget) n -= 16;
-    return n;
-}
+uint32_t cfg_capacity(const sasa_b200_ctx *, const SmallCfg &c, bool has_cls) { return c.cap[has_cls ? 1 : 0]; }
 
 struct Launch {
     int cfg;          // index into ctx->cfgs, or -1 for the large-structure path
@@ -411,7 +396,7 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
         const bool has_cls = (variant & 1) == 1;
         kp.nmax = cfg_capacity(ctx, c, has_cls);
         kp.cmax = c.cmax;
-        const size_t smem = small_layout(kp.nmax, kp.cmax, c.nt / 32, has_cls).total;
+        const size_t smem = c.smem[has_cls ? 1 : 0];
         const int grid = (int)std::min<uint32_t>(L.n_work, (uint32_t)(ctx->sm_count * c.minb));
         cudaStream_t ls = st;
         if (fork && small_idx > 0) {

@@ -37,8 +37,8 @@ __host__ __device__ constexpr size_t small_fixed_bytes(int nwarps) {
            32 * 8 * 4 + 64;
 }
 
-__host__ __device__ inline SmallLayout small_layout(uint32_t nmax, uint32_t cmax, int nwarps, bool has_cls) {
-    SmallLayout L;
+__host__ __device__ constexpr SmallLayout small_layout(uint32_t nmax, uint32_t cmax, int nwarps, bool has_cls) {
+    SmallLayout L{};
     size_t o = 0;
     L.pts = o;   o += 128 * 16;
     L.ent = o;   o += (size_t)nwarps * kNbCap * 16;
@@ -54,6 +54,24 @@ __host__ __device__ inline SmallLayout small_layout(uint32_t nmax, uint32_t cmax
     L.cellw = o; o += (((size_t)cmax + 2 + 1) / 2) * 4;
     L.total = (o + 15) & ~(size_t)15;
     return L;
+}
+
+// Capacities are compile-time constants of a configuration (threads, CTAs per SM, cell-table size): B200 has 228 KB of
+// shared memory per SM, 1 KB of it reserved per resident CTA, and at most 227 KB per CTA.  With constant capacities
+// every region of the layout sits at an immediate offset, which frees the registers a run-time layout would pin.
+constexpr size_t kSmemPerSM = 228 * 1024, kSmemPerCtaMax = 227 * 1024, kSmemCtaReserve = 1024;
+__host__ __device__ constexpr size_t cta_budget(int minb) {
+    return kSmemPerSM / (size_t)minb - kSmemCtaReserve < kSmemPerCtaMax ? kSmemPerSM / (size_t)minb - kSmemCtaReserve : kSmemPerCtaMax;
+}
+// Largest atom capacity (multiple of 16, < 65520 for the u16 indices) whose layout fits the budget of the configuration.
+__host__ __device__ constexpr uint32_t max_atoms(int nt, int minb, uint32_t cmax, bool has_cls) {
+    uint32_t lo = 0, hi = 65520 / 16 - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) / 2;
+        if (small_layout(mid * 16, cmax, nt / 32, has_cls).total <= cta_budget(minb)) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo * 16;
 }
 
 // min or max of 8 per-thread values over the block; result valid in every thread.
@@ -101,10 +119,10 @@ struct SmemView {
     uint16_t *cell;     // cell table: start position of every cell, cell[ncell] = N
 };
 
-template <int NT, bool HAS_CLS>
-__device__ __forceinline__ SmemView smem_view(unsigned char *smem, const KParams &p) {
+template <int NT, bool HAS_CLS, uint32_t NMAX, uint32_t CMAX>
+__device__ __forceinline__ SmemView smem_view(unsigned char *smem) {
     constexpr int NW = NT / 32;
-    const SmallLayout L = small_layout(p.nmax, p.cmax, NW, HAS_CLS);
+    constexpr SmallLayout L = small_layout(NMAX, CMAX, NW, HAS_CLS);
     SmemView v;
     v.ptab = reinterpret_cast<float4 *>(smem);
     v.atom = reinterpret_cast<float4 *>(smem + small_fixed_bytes(NW));
@@ -112,7 +130,7 @@ __device__ __forceinline__ SmemView smem_view(unsigned char *smem, const KParams
     v.misc = reinterpret_cast<int *>(smem + L.misc);
     v.val = reinterpret_cast<float *>(smem + L.val);
     v.cellid = reinterpret_cast<uint16_t *>(smem + L.val);
-    v.rank = v.cellid + p.nmax;
+    v.rank = v.cellid + NMAX;
     v.cls = HAS_CLS ? reinterpret_cast<uint32_t *>(smem + L.cls) : nullptr;
     v.orig = reinterpret_cast<uint16_t *>(smem + L.orig);
     v.cellw = reinterpret_cast<uint32_t *>(smem + L.cellw);
@@ -133,7 +151,7 @@ __device__ __forceinline__ void stage_points(const KParams &p, float4 *ptab) {
 // block reduction), the cell grid, a counting sort with shared-memory atomics and the exclusive scan of the
 // cell counts.  Replaces SpatialGrid::new (src/structures/spatial_grid.rs:28-106).  Returns false when the
 // structure holds a non-finite value (outputs are then NaN-filled and the error flag raised).
-template <int NT, bool HAS_CLS>
+template <int NT, bool HAS_CLS, uint32_t CMAX>
 __device__ __forceinline__ bool structure_setup(const KParams &p, const SmemView &V, uint32_t sid, uint32_t a0, int N,
                                                 Grid &g, int &ncell) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -172,8 +190,8 @@ __device__ __forceinline__ bool structure_setup(const KParams &p, const SmemView
         for (int it = 0; it < 64; ++it) {
             fx = floorf(ex / c) + 1.0f; fy = floorf(ey / c) + 1.0f; fz = floorf(ez / c) + 1.0f;
             const float nc = fx * fy * fz;
-            if (nc <= (float)p.cmax) break;
-            c *= fmaxf(1.05f, cbrtf(nc / (float)p.cmax));
+            if (nc <= (float)CMAX) break;
+            c *= fmaxf(1.05f, cbrtf(nc / (float)CMAX));
         }
         g.minx = mnx; g.miny = mny; g.minz = mnz;
         g.inv_c = 1.0f / c;
@@ -294,12 +312,13 @@ __device__ __forceinline__ bool claim_structure(const KParams &p, int *misc, uin
 // ---------------------------------------------------------------------------------------------------------
 // Generic fused kernel: any n_points (128-point chunks), boundary statistics, forced streaming.
 // ---------------------------------------------------------------------------------------------------------
-template <int NT, int MINB, bool HAS_CLS>
+template <int NT, int MINB, bool HAS_CLS, uint32_t CMAX>
 __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NW = NT / 32;
+    constexpr uint32_t NMAX = max_atoms(NT, MINB, CMAX, HAS_CLS);
     constexpr size_t kOffEnt = 128 * 16, kOffCand = kOffEnt + (size_t)NW * kNbCap * 16;
-    const SmemView V = smem_view<NT, HAS_CLS>(smem, p);
+    const SmemView V = smem_view<NT, HAS_CLS, NMAX, CMAX>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *const w_ent = reinterpret_cast<float4 *>(smem + kOffEnt) + warp * kNbCap;
     uint16_t *const w_cand = reinterpret_cast<uint16_t *>(smem + kOffCand) + warp * kQueueCap;
@@ -312,7 +331,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
     while (claim_structure(p, V.misc, sid, a0, N)) {
         Grid g;
         int ncell;
-        if (!structure_setup<NT, HAS_CLS>(p, V, sid, a0, N, g, ncell)) continue;
+        if (!structure_setup<NT, HAS_CLS, CMAX>(p, V, sid, a0, N, g, ncell)) continue;
 
         // ---- per-atom work: warps pull runs of consecutive cell-sorted atoms from a shared counter ----------
         const SmemAtoms atoms{V.atom};

@@ -251,13 +251,14 @@ __device__ __noinline__ int tight_cold_atom(const float *px, const float *py, co
     return (int)atom_streaming<SmemAtoms, uint16_t, false>(q, g, atoms, s_cell, cls, pos, ent, nullptr);
 }
 
-template <int NT, int MINB, bool HAS_CLS>
+template <int NT, int MINB, bool HAS_CLS, uint32_t CMAX>
 __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NW = NT / 32;
+    constexpr uint32_t NMAX = max_atoms(NT, MINB, CMAX, HAS_CLS);
     constexpr size_t kOffEnt = 128 * 16, kOffCand = kOffEnt + (size_t)NW * kNbCap * 16,
                      kOffList = kOffCand + (size_t)NW * kQueueCap * 2;
-    const SmemView V = smem_view<NT, HAS_CLS>(smem, p);
+    const SmemView V = smem_view<NT, HAS_CLS, NMAX, CMAX>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *const w_ent = reinterpret_cast<float4 *>(smem + kOffEnt) + warp * kNbCap;
     uint16_t *const w_cand = reinterpret_cast<uint16_t *>(smem + kOffCand) + warp * kQueueCap;
@@ -272,16 +273,23 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
     while (claim_structure(p, V.misc, sid, a0, N)) {
         Grid g;
         int ncell;
-        if (!structure_setup<NT, HAS_CLS>(p, V, sid, a0, N, g, ncell)) continue;
+        if (!structure_setup<NT, HAS_CLS, CMAX>(p, V, sid, a0, N, g, ncell)) continue;
 
         // ---- per-atom work: warps claim runs of consecutive cells; the atoms of a cell share its candidate list ----
         unsigned pairs = 0, streamed = 0;
         for (;;) {
-            int c0 = 0;
-            if (lane == 0) c0 = atomicAdd(&V.misc[1], SASA_CELL_FETCH);
+            // guided self-scheduling: long runs of cells while plenty remain, short ones near the end of the structure
+            // (any positive increment partitions the cells, so the stale read of the counter is harmless)
+            int c0 = 0, take = 0;
+            if (lane == 0) {
+                const int left = ncell - *(volatile int *)&V.misc[1];
+                take = max(SASA_CELL_FETCH, min(8 * SASA_CELL_FETCH, left / (4 * NW)));
+                c0 = atomicAdd(&V.misc[1], take);
+            }
             c0 = __shfl_sync(kFull, c0, 0);
+            take = __shfl_sync(kFull, take, 0);
             if (c0 >= ncell) break;
-            const int c1 = min(c0 + SASA_CELL_FETCH, ncell);
+            const int c1 = min(c0 + take, ncell);
             int pos = (int)V.cell[c0];
             const int pos_end = (int)V.cell[c1];
             while (pos < pos_end) {
