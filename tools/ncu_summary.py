@@ -40,10 +40,13 @@ def to_bytes(value, unit):
     return float(value.replace(",", "")) * scale.get(unit, 1.0)
 
 
-def traffic(rep, structures, out):
-    """--traffic: profiles/ncu_traffic.json for bench.py (DRAM bytes of the captured step = sum over its launches)."""
+def traffic(rep, structures, out, per_step=0):
+    """--traffic: profiles/ncu_traffic.json for bench.py (DRAM bytes of ONE step = sum over its launches; per_step > 0:
+    the capture holds several steps of per_step launches each, keep the first)."""
     import json
     hdr, units, rows = raw(rep)
+    if per_step:
+        rows = rows[:per_step]
     col = {h: i for i, h in enumerate(hdr)}
     total, per = 0.0, []
     for r in rows:
@@ -57,7 +60,7 @@ def traffic(rep, structures, out):
 
 def main():
     if sys.argv[1] == "--traffic":
-        return traffic(sys.argv[2], int(sys.argv[3]), sys.argv[4])
+        return traffic(sys.argv[2], int(sys.argv[3]), sys.argv[4], int(sys.argv[5]) if len(sys.argv) > 5 else 0)
     rep = sys.argv[1]
     hdr, units, rows = raw(rep)
     col = {h: i for i, h in enumerate(hdr)}
