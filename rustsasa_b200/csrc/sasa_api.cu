@@ -131,15 +131,22 @@ struct Proto {
     int nt, minb;
     uint32_t cmax;
     uint32_t cap[2];     // max_atoms(...) without / with id classes
-    SmallKernel fn[4];   // index = has_cls + 2 * tight (tight: n_points <= 128, no statistics / forced streaming)
+    SmallKernel fn[6];   // index = has_cls + 2 * tight (tight: n_points <= 128, no statistics / forced streaming)
+                         //         + 2 more when the tight kernel compiled for 3 body slots applies (65..96 body points)
 };
 #define SASA_PROTO(NT, MINB, CMAX)                                                                                     \
     Proto { NT, MINB, CMAX, { max_atoms(NT, MINB, CMAX, false), max_atoms(NT, MINB, CMAX, true) },                     \
             { sasa_small_kernel<NT, MINB, false, CMAX>, sasa_small_kernel<NT, MINB, true, CMAX>,                       \
-              sasa_tight_kernel<NT, MINB, false, CMAX>, sasa_tight_kernel<NT, MINB, true, CMAX> } }
+              sasa_tight_kernel<NT, MINB, false, CMAX, 0>, sasa_tight_kernel<NT, MINB, true, CMAX, 0>,                 \
+              sasa_tight_kernel<NT, MINB, false, CMAX, 3>, sasa_tight_kernel<NT, MINB, true, CMAX, 3> } }
 // 0-2 keep 32 warps resident per SM (64 registers/thread); 3-4 keep 24 warps (85 registers/thread)
+#ifdef SASA_DEFAULT_PROTOS_ONLY   // quick builds of tuning variants: only the default configurations are instantiated
+const Proto kProtos[] = {SASA_PROTO(512, 2, 8192), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384),
+                         SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384)};
+#else
 const Proto kProtos[] = {SASA_PROTO(256, 4, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384),
                          SASA_PROTO(384, 2, 8192), SASA_PROTO(768, 1, 16384)};
+#endif
 const char *kDefaultCfgs = "12";
 constexpr int kNumProtos = sizeof(kProtos) / sizeof(kProtos[0]);
 
@@ -154,7 +161,7 @@ int build_cfgs(sasa_b200_ctx *ctx) {
         if (c.cap[0] == 0 || c.cap[1] == 0 || std::max(c.smem[0], c.smem[1]) > ctx->smem_optin)
             return fail(ctx, SASA_B200_ERR_UNSUPPORTED, "the fused kernels are laid out for 228 KB of shared memory per SM (B200); this device offers %zu per block",
                         ctx->smem_optin);
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < 6; ++v) {
             cudaError_t e = cudaFuncSetAttribute((const void *)pr.fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem[v & 1]);
             if (e != cudaSuccess)
                 return fail(ctx, SASA_B200_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", c.smem[v & 1], cudaGetErrorString(e));
@@ -404,7 +411,10 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
             CU_TRY(ctx, cudaStreamWaitEvent(ls, ctx->ev_fork, 0));
         }
         void *args[] = {(void *)&kp};
-        cudaError_t e = cudaLaunchKernel((const void *)kProtos[c.proto].fn[(has_cls ? 1 : 0) + ((kp.n_points <= 128 && (kp.flags & 3u) == 0) ? 2 : 0)], dim3(grid), dim3(c.nt), args, smem, ls);
+        const bool tight = kp.n_points <= 128 && (kp.flags & 3u) == 0;
+        const uint32_t body = std::min(kp.n_points, kp.n_body);
+        const int which = (has_cls ? 1 : 0) + (tight ? (SASA_OPT_NSLT && body > 64 && body <= 96 ? 4 : 2) : 0);
+        cudaError_t e = cudaLaunchKernel((const void *)kProtos[c.proto].fn[which], dim3(grid), dim3(c.nt), args, smem, ls);
         if (e != cudaSuccess) return fail(ctx, SASA_B200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
         if (ls != st) {
             CU_TRY(ctx, cudaEventRecord(ctx->ev_join[small_idx - 1], ls));

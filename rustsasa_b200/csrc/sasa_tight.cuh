@@ -25,6 +25,20 @@ namespace sasa {
 #ifndef SASA_CELL_FETCH
 #define SASA_CELL_FETCH 4
 #endif
+// tuning switches (tools/variants.py builds A/B libraries with -D overrides)
+#ifndef SASA_OPT_FILL4
+#define SASA_OPT_FILL4 1      // fill_list: four positions per trip
+#endif
+#ifndef SASA_OPT_P1U
+#define SASA_OPT_P1U 4        // phase 1: entries per unrolled trip
+#endif
+#ifndef SASA_OPT_TAILX
+#define SASA_OPT_TAILX 0      // tail tiles: nearest N entries tested on their own first (0: one pass over all entries).
+                              // Measured (gpurun_out v1/v2, cfg2): 16 costs ~30 warp instructions per atom more than it saves.
+#endif
+#ifndef SASA_OPT_NSLT
+#define SASA_OPT_NSLT 1       // launch the kernel compiled for 3 body slots when it applies
+#endif
 
 // Flatten the candidate rows of cell (cx, cy, cz) into list[0, total) (positions in the sorted atom array),
 // padded with `sentinel` up to the next multiple of 32.  Returns total, or -1 when it exceeds kListCap.
@@ -50,10 +64,24 @@ __device__ __forceinline__ int tight_fill_list(const Grid &g, const uint16_t *ce
     const int total = __shfl_sync(kFull, incl, 31);
     if (total > kListCap) return -1;
     const int maxlen = __reduce_max_sync(kFull, len);
+    // row expansion, four positions per trip (the longest row of a protein-density cell block holds ~13 atoms)
+#if SASA_OPT_FILL4
+    uint16_t *dst = list + (incl - len);
+    int v = start, left = len;
+#pragma unroll 1
+    for (int t = 0; t < maxlen; t += 4) {
+        if (left > 0) dst[0] = (uint16_t)v;
+        if (left > 1) dst[1] = (uint16_t)(v + 1);
+        if (left > 2) dst[2] = (uint16_t)(v + 2);
+        if (left > 3) dst[3] = (uint16_t)(v + 3);
+        dst += 4; v += 4; left -= 4;
+    }
+#else
     uint16_t *dst = list + (incl - len);
 #pragma unroll 1
     for (int t = 0; t < maxlen; ++t)
         if (t < len) dst[t] = (uint16_t)(start + t);
+#endif
     const int pad = total + lane;
     if (pad < ((total + 31) & ~31)) list[pad] = (uint16_t)sentinel;
     __syncwarp();
@@ -125,9 +153,11 @@ __device__ __forceinline__ void tight_phase1(const float4 *ent, int m, const flo
     if (NSL > 3) p3 = pts[96 + lane];
     // scalar flags so that ptxas keeps them in predicate registers: FSETP.LT.OR P, dot, limit, P
     bool o0 = lane >= nbody, o1 = 32 + lane >= nbody, o2 = 64 + lane >= nbody, o3 = 96 + lane >= nbody;
-#pragma unroll 2
-    for (int q = 0; q < m; ++q) {
-        const float4 e = ent[q];
+    const float4 *const eend = ent + m;
+    constexpr int kUnroll = SASA_OPT_P1U;
+#pragma unroll kUnroll
+    for (const float4 *ep = ent; ep < eend; ++ep) {
+        const float4 e = *ep;
         o0 = o0 || (dot_body(p0.x, p0.y, p0.z, e) < e.w);
         if (NSL > 1) o1 = o1 || (dot_body(p1.x, p1.y, p1.z, e) < e.w);
         if (NSL > 2) o2 = o2 || (dot_body(p2.x, p2.y, p2.z, e) < e.w);
@@ -143,10 +173,10 @@ __device__ __forceinline__ void tight_phase1(const float4 *ent, int m, const flo
 // (l mod G) and entry offset (l div G), so one step tests 32/G entries against every point.
 __device__ __forceinline__ int tile_shift(int ns) { return 32 - __clz(ns - 1); }   // ns = 1 -> clz(0) = 32 -> 0
 
-// `pt` (this lane's point of the tile) against entries [q0, k).  Returns how many of the ns points no entry
-// occludes.  Every lane runs the same number of full steps (unrollable); the ragged last step is predicated.
+// `pt` (this lane's point of the tile) against entries [q0, k).  Returns the mask of occluded points (bit g = point g
+// of the tile, g < 2^sh).  Every lane runs the same number of full steps (unrollable); the ragged last step is predicated.
 template <bool TAIL>
-__device__ __forceinline__ int tight_tile(const float4 *ent, int q0, int k, const float4 pt, int sh, int ns) {
+__device__ __forceinline__ unsigned tight_tile(const float4 *ent, int q0, int k, const float4 pt, int sh) {
     const int lane = lane_id();
     const int kstep = 32 >> sh;
     const float4 *ep = ent + q0 + (lane >> sh);
@@ -170,10 +200,15 @@ __device__ __forceinline__ int tight_tile(const float4 *ent, int q0, int k, cons
     }
     const bool hit = TAIL ? (best >= 0.0f) : (best > 0.0f);
     // OR over the lanes that share a point: one REDUX.OR of per-point bits
-    const unsigned hm = __reduce_or_sync(kFull, hit ? (1u << (lane & ((1 << sh) - 1))) : 0u);
-    const unsigned valid = ns >= 32 ? 0xffffffffu : ((1u << ns) - 1u);
-    return __popc(~hm & valid);
+    return __reduce_or_sync(kFull, hit ? (1u << (lane & ((1 << sh) - 1))) : 0u);
 }
+
+// The first ns (1..32) bits set.
+__device__ __forceinline__ unsigned low_bits(int ns) { return 0xffffffffu >> (32 - ns); }
+
+// Optional staging of tail tiles (off by default): test the kTailFirst nearest entries on their own and the rest only
+// while some tail point is still exposed.
+constexpr int kTailFirst = SASA_OPT_TAILX;
 
 // One atom with its complete neighbour list in ent[0, k), nfront near entries first.  nbody = body points
 // (index < n_body), the tail points are [nbody, n_points); tail_sh = tile_shift(min(32, ntail)).
@@ -203,7 +238,7 @@ __device__ __forceinline__ int tight_atom(const KParams &p, const float4 *ent, i
             const int nb = min(32, ns - b);
             const int sh = tile_shift(nb);
             const int sidx = lane & ((1 << sh) - 1);
-            exposed += tight_tile<false>(ent, m, k, pts[sidx < nb ? (int)queue[b + sidx] : 0], sh, nb);
+            exposed += __popc(~tight_tile<false>(ent, m, k, pts[sidx < nb ? (int)queue[b + sidx] : 0], sh) & low_bits(nb));
         }
         __syncwarp();
     }
@@ -217,7 +252,16 @@ __device__ __forceinline__ int tight_atom(const KParams &p, const float4 *ent, i
             for (int t0 = 0; t0 < ntail; t0 += 32) {
                 const int nt = min(32, ntail - t0);
                 // the last batch of a long tail may be narrower than the tile: its surplus lanes re-test point 0
-                exposed += tight_tile<true>(ent, 0, k, pts[nbody + t0 + (sidx < nt ? sidx : 0)], tail_sh, nt);
+                const float4 pt = pts[nbody + t0 + (sidx < nt ? sidx : 0)];
+                const unsigned valid = low_bits(nt);
+                unsigned hm = 0u;
+                int q0 = 0, q1 = kTailFirst > 0 ? min(k, kTailFirst) : k;
+                do {   // the nearest entries first; the rest only while some tail point is still exposed
+                    hm |= tight_tile<true>(ent, q0, q1, pt, tail_sh);
+                    q0 = q1;
+                    q1 = k;
+                } while (q0 < k && (~hm & valid) != 0u);
+                exposed += __popc(~hm & valid);
             }
         }
     }
@@ -251,7 +295,9 @@ __device__ __noinline__ int tight_cold_atom(const float *px, const float *py, co
     return (int)atom_streaming<SmemAtoms, uint16_t, false>(q, g, atoms, s_cell, cls, pos, ent, nullptr);
 }
 
-template <int NT, int MINB, bool HAS_CLS, uint32_t CMAX>
+// NSLT: number of 32-point body slots the kernel is compiled for (3 = the reference's default of 100 points on 8- and
+// 16-lane builds, 96 body points), or 0 to choose per launch among 1..4.
+template <int NT, int MINB, bool HAS_CLS, uint32_t CMAX, int NSLT>
 __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NW = NT / 32;
@@ -308,7 +354,8 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                         const float r = __fadd_rn(ai.w, p.probe);
                         const int nfront = tight_entries(V.atom, ai, p.probe, __fmul_rn(r, r), __fmul_rn(2.0f, r), p.near2,
                                                          w_cand, k, w_ent);
-                        if (nsl == 3) cnt = tight_atom<3>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
+                        if (NSLT > 0) cnt = tight_atom<NSLT ? NSLT : 1>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
+                        else if (nsl == 3) cnt = tight_atom<3>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
                         else if (nsl == 4) cnt = tight_atom<4>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
                         else if (nsl == 2) cnt = tight_atom<2>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
                         else cnt = tight_atom<1>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
