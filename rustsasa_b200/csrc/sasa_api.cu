@@ -35,7 +35,8 @@ namespace {
 thread_local std::string g_create_error;
 
 struct Points {
-    float *d = nullptr;  // 3*n floats: x[n] y[n] z[n]
+    float *d = nullptr;    // 3*n floats: x[n] y[n] z[n]
+    uint4 *cap = nullptr;  // cap table (sasa_cap.cuh), n <= 128 only
 };
 
 struct SmallCfg {
@@ -110,7 +111,7 @@ void sphere_points_host(uint32_t n, float *x, float *y, float *z) {
     }
 }
 
-int get_points(sasa_b200_ctx *ctx, uint32_t n, const float **px) {
+int get_points(sasa_b200_ctx *ctx, uint32_t n, const float **px, const uint4 **cap) {
     auto it = ctx->points.find(n);
     if (it == ctx->points.end()) {
         std::vector<float> h(3 * (size_t)n);
@@ -118,9 +119,16 @@ int get_points(sasa_b200_ctx *ctx, uint32_t n, const float **px) {
         Points P;
         CU_TRY(ctx, cudaMalloc(&P.d, h.size() * sizeof(float)));
         CU_TRY(ctx, cudaMemcpy(P.d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (n <= 128) {   // the point sets of the tight kernel get their cap table (built once per context and n_points)
+            std::vector<uint32_t> t(kCapBins * 8);
+            cap_build_table(n, h.data(), h.data() + n, h.data() + 2 * (size_t)n, t.data());
+            CU_TRY(ctx, cudaMalloc(&P.cap, t.size() * sizeof(uint32_t)));
+            CU_TRY(ctx, cudaMemcpy(P.cap, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
         it = ctx->points.emplace(n, P).first;
     }
     *px = it->second.d;
+    *cap = it->second.cap;
     return SASA_B200_OK;
 }
 
@@ -318,6 +326,7 @@ struct RunArgs {
     sasa_b200_outputs d_out;
     sasa_b200_params prm;
     const float *d_points;
+    const uint4 *d_cap;
 };
 
 int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
@@ -334,6 +343,7 @@ int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
     kp->out_seg = b->n_seg ? ra.d_out.seg_sasa : nullptr;
     kp->out_protein = ra.d_out.protein;
     const uint32_t n = ra.prm.n_points;
+    kp->cap = ra.d_cap;
     kp->px = ra.d_points;
     kp->py = ra.d_points + n;
     kp->pz = ra.d_points + 2 * (size_t)n;
@@ -511,7 +521,7 @@ void sasa_b200_destroy(sasa_b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (auto &kv : ctx->points) cudaFree(kv.second.d);
+    for (auto &kv : ctx->points) { cudaFree(kv.second.d); cudaFree(kv.second.cap); }
     for (int i = 0; i < kStreams; ++i)
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
     for (int i = 0; i < sasa_b200_ctx::kSide; ++i) {
@@ -653,7 +663,7 @@ int sasa_b200_batch_run_device(sasa_b200_batch *b, const float *d_xyzr, const ui
     ra.d_cls = d_id_class;
     ra.d_out = *d_out;
     ra.prm = *params;
-    if ((rc = get_points(ctx, params->n_points, &ra.d_points)) != 0) return rc;
+    if ((rc = get_points(ctx, params->n_points, &ra.d_points, &ra.d_cap)) != 0) return rc;
     const int variant = (d_id_class ? 1 : 0) + 2;
     KParams base;
     make_kparams(b, ra, &base);
@@ -719,7 +729,7 @@ static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz
     ra.d_out.seg_sasa = (out->seg_sasa && G) ? reinterpret_cast<float *>(base_p + o_seg) : nullptr;
     ra.d_out.protein = out->protein ? reinterpret_cast<float *>(base_p + o_prot) : nullptr;
     ra.prm = *params;
-    if ((rc = get_points(ctx, params->n_points, &ra.d_points)) != 0) return rc;
+    if ((rc = get_points(ctx, params->n_points, &ra.d_points, &ra.d_cap)) != 0) return rc;
     KParams kbase;
     make_kparams(b, ra, &kbase);
     b->launches_last = 0;
@@ -819,7 +829,7 @@ static int run_atom_range_locked(sasa_b200_batch *b, const float *d_xyzr, const 
     ra.d_cls = d_cls;
     ra.d_out = sasa_b200_outputs{d_counts, d_atom, nullptr, nullptr};
     ra.prm = *params;
-    if ((rc = get_points(ctx, params->n_points, &ra.d_points)) != 0) return rc;
+    if ((rc = get_points(ctx, params->n_points, &ra.d_points, &ra.d_cap)) != 0) return rc;
     KParams kp;
     make_kparams(b, ra, &kp);
     kp.seg_be = nullptr;

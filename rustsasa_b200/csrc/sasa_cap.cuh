@@ -1,0 +1,185 @@
+// sasa_cap.cuh -- cap-table occlusion: the exact Shrake-Rupley point test with (almost) no point tests.
+//
+// Neighbour j occludes a spherical cap of atom i's test sphere: the reference's test dot(p, v) < limit
+// (src/lib.rs:128-147; v = c_i - c_j) is p . v^ < c with c = limit / |v|.  For a fixed point set the answer depends
+// only on the direction v^ and the level c, so it is tabulated: v^ is binned on an octahedral N x N grid, c on L
+// uniform levels of [-1, 1] (plus one level below and one above), and every bin holds two point masks
+//     inner : points occluded for EVERY (v^, c) of the bin  -> decided without arithmetic
+//     ring  : points occluded for SOME but not all          -> decided by the reference's exact test
+// and points in neither are exposed to this neighbour for every (v^, c) of the bin.  Per atom, one lane per neighbour
+// looks its bin up (32 B from L2), the inner masks are OR-reduced across the warp, and only (ring point, neighbour)
+// pairs whose point is still uncovered run the exact arithmetic of sasa_device.cuh -- about 10-25 tests per atom
+// instead of ~1,500 (tools/cap_model.py).  The result is the reference's, bit for bit: the table never decides a
+// point the exact test could decide differently, because the bins are built in double precision with a margin
+// (kCapEpsAng on the direction, kCapEpsC on the level) that is 100x the worst float rounding of the binning
+// arithmetic below and of the reference's own dot product, and 100x smaller than a bin.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "sasa_device.cuh"
+
+#ifndef SASA_CAP_N
+#define SASA_CAP_N 64          // direction bins per axis of the octahedral square (even)
+#endif
+#ifndef SASA_CAP_L
+#define SASA_CAP_L 64          // level bins over c in [-1, 1]
+#endif
+
+namespace sasa {
+
+constexpr int kCapN = SASA_CAP_N, kCapL = SASA_CAP_L;
+constexpr int kCapLevels = kCapL + 2;                       // level 0: c < -1, level L + 1: c >= 1
+constexpr size_t kCapBins = (size_t)kCapLevels * kCapN * kCapN;
+constexpr double kCapEpsAng = 1.0e-3;                        // radians added to every direction bin's radius
+constexpr double kCapEpsC = 1.0e-4;                          // widening of every level interval
+constexpr float kCapMinV2 = 1.0e-6f;                         // |v|^2 below this: no table, every point takes the exact test
+
+// ---- host: the table of one point set (n <= 128), 2 x uint4 per bin: {inner, ring} -------------------------------------
+// Direction bin (iu, iv) is the cell [-1 + 2 iu/N, -1 + 2 (iu+1)/N] x [...] of the octahedral square.  Its cell
+// edges are great-circle arcs (u = const is a plane through the origin inside each octant; with N even the octant
+// boundaries and the fold |u| + |v| = 1 run through grid nodes), so the largest angle between the cell centre and any
+// direction of the cell is attained at one of the four corners: rho = max corner angle + kCapEpsAng.  For a point at
+// angle alpha from the centre, p . u over the cell lies within [cos(min(alpha + rho, pi)), cos(max(alpha - rho, 0))].
+inline void cap_oct_dir(double u, double v, double d[3]) {
+    const double z = 1.0 - std::fabs(u) - std::fabs(v);
+    double x = u, y = v;
+    if (z < 0.0) {
+        x = (1.0 - std::fabs(v)) * (u >= 0.0 ? 1.0 : -1.0);
+        y = (1.0 - std::fabs(u)) * (v >= 0.0 ? 1.0 : -1.0);
+    }
+    const double inv = 1.0 / std::sqrt(x * x + y * y + z * z);
+    d[0] = x * inv; d[1] = y * inv; d[2] = z * inv;
+}
+
+inline void cap_build_table(uint32_t n, const float *px, const float *py, const float *pz, uint32_t *tab /* 8 * kCapBins */) {
+    const int N = kCapN, L = kCapL;
+    memset(tab, 0, kCapBins * 8 * sizeof(uint32_t));
+    // level l covers c in [lo(l), hi(l)): lo(0) = -inf, lo(l) = -1 + 2 (l - 1) / L, hi(l) = lo(l + 1), hi(L + 1) = +inf
+    std::vector<double> lo(kCapLevels), hi(kCapLevels);
+    for (int l = 0; l < kCapLevels; ++l) {
+        lo[l] = l == 0 ? -INFINITY : -1.0 + 2.0 * (l - 1) / L;
+        hi[l] = l == kCapLevels - 1 ? INFINITY : -1.0 + 2.0 * l / L;
+    }
+    for (int iv = 0; iv < N; ++iv)
+        for (int iu = 0; iu < N; ++iu) {
+            const double u0 = -1.0 + 2.0 * iu / N, u1 = -1.0 + 2.0 * (iu + 1) / N;
+            const double v0 = -1.0 + 2.0 * iv / N, v1 = -1.0 + 2.0 * (iv + 1) / N;
+            double c[3], k[3];
+            cap_oct_dir(0.5 * (u0 + u1), 0.5 * (v0 + v1), c);
+            double rho = 0.0;
+            const double cu[4] = {u0, u1, u0, u1}, cv[4] = {v0, v0, v1, v1};
+            for (int t = 0; t < 4; ++t) {
+                cap_oct_dir(cu[t], cv[t], k);
+                rho = std::max(rho, std::acos(std::min(1.0, std::max(-1.0, c[0] * k[0] + c[1] * k[1] + c[2] * k[2]))));
+            }
+            rho += kCapEpsAng;
+            for (uint32_t p = 0; p < n; ++p) {
+                // normalise the float point (it is unit length only to float rounding)
+                const double x = px[p], y = py[p], z = pz[p], len = std::sqrt(x * x + y * y + z * z);
+                const double alpha = std::acos(std::min(1.0, std::max(-1.0, (c[0] * x + c[1] * y + c[2] * z) / len)));
+                // the device compares the UNnormalised point: p . v^ = len * cos(angle)
+                const double dmax = len * std::cos(std::max(alpha - rho, 0.0)), dmin = len * std::cos(std::min(alpha + rho, M_PI));
+                const uint32_t bit = 1u << (p & 31);
+                for (int l = 0; l < kCapLevels; ++l) {
+                    const bool inner = dmax < lo[l] - kCapEpsC;      // occluded whatever (v^, c) of the bin
+                    const bool outer = dmin < hi[l] + kCapEpsC;      // occluded for some (v^, c) of the bin
+                    uint32_t *e = tab + (((size_t)l * N + iv) * N + iu) * 8;
+                    if (inner) e[p >> 5] |= bit;
+                    else if (outer) e[4 + (p >> 5)] |= bit;
+                }
+            }
+        }
+}
+
+// ---- device ------------------------------------------------------------------------------------------------------------
+// Bin of entry e = (vx, vy, vz, limit) with vmag = |v|^2 >= kCapMinV2.  Approximate reciprocals are fine here: the bins'
+// margins absorb 1e-4 in c and 1e-3 rad in direction, these errors are ~1e-6.
+__device__ __forceinline__ int cap_bin(const float4 e, float vmag) {
+    const float c = e.w * rsqrtf(vmag);
+    const float s = __fdividef(1.0f, fabsf(e.x) + fabsf(e.y) + fabsf(e.z));
+    float u = e.x * s, v = e.y * s;
+    if (e.z < 0.0f) {
+        const float uu = copysignf(1.0f - fabsf(v), u);
+        v = copysignf(1.0f - fabsf(u), v);
+        u = uu;
+    }
+    // __float2int_rd saturates and maps NaN to 0; the clamps make every input land in a valid bin
+    const int iu = min(max(__float2int_rd(fmaf(u, 0.5f * kCapN, 0.5f * kCapN)), 0), kCapN - 1);
+    const int iv = min(max(__float2int_rd(fmaf(v, 0.5f * kCapN, 0.5f * kCapN)), 0), kCapN - 1);
+    const int l = min(max(__float2int_rd(fmaf(c, 0.5f * kCapL, 0.5f * kCapL)) + 1, 0), kCapLevels - 1);
+    return (l * kCapN + iv) * kCapN + iu;
+}
+
+// Exact tests of this lane's neighbour e against the points of word W (points 32 W .. 32 W + 31) set in m.
+// Returns the mask of points found occluded.  MIXED: the word may hold tail points (index >= nbody: unfused dot, <=).
+template <int W, bool MIXED>
+__device__ __forceinline__ unsigned cap_ring_word(unsigned m, const float4 e, const float4 *pts, int nbody) {
+    unsigned hit = 0u;
+    while (__any_sync(kFull, m != 0u)) {
+        if (m) {
+            const int b = 31 - __clz(m);
+            const unsigned bit = 1u << b;
+            m ^= bit;
+            const float4 P = pts[32 * W + b];
+            bool oc;
+            if (MIXED && 32 * W + b >= nbody) oc = dot_tail(P.x, P.y, P.z, e) <= e.w;
+            else oc = dot_body(P.x, P.y, P.z, e) < e.w;
+            if (oc) hit |= bit;
+        }
+    }
+    return hit;
+}
+
+template <int W>
+__device__ __forceinline__ unsigned cap_ring(unsigned m, const float4 e, const float4 *pts, int nbody) {
+    if (32 * W + 32 <= nbody) return cap_ring_word<W, false>(m, e, pts, nbody);
+    return cap_ring_word<W, true>(m, e, pts, nbody);
+}
+
+// The first min(max(n, 0), 32) bits set.
+__device__ __forceinline__ unsigned cap_first_bits(int n) { return n <= 0 ? 0u : n >= 32 ? 0xffffffffu : (1u << n) - 1u; }
+
+// One atom: neighbours cand[0, k) (positions in the cell-sorted shared atom array).  Returns the exposed-point count.
+// Lane q of round r owns neighbour 32 r + q: it builds the entry with the reference's arithmetic (make_entry), fetches
+// its bin's masks, and -- after the warp-wide OR of the inner masks -- runs the exact test on its own ring points that
+// are still uncovered.  Hits are folded into the next OR.
+__device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const float4 *s_atom, const float4 ai, float probe,
+                                        const uint16_t *cand, int k, const float4 *pts, int n_points, int nbody) {
+    const int lane = lane_id();
+    const float r = __fadd_rn(ai.w, probe);
+    const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
+    unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;      // this lane's inner masks and exact hits, not yet reduced
+#pragma unroll 1
+    for (int q0 = 0; q0 < k; q0 += 32) {
+        const int q = q0 + lane;
+        const bool valid = q < k;
+        const float4 aj = s_atom[valid ? (int)cand[q] : 0];
+        float vmag;
+        const float4 e = make_entry(ai, aj, probe, r2, two_r, &vmag);
+        uint4 rg = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+            if (vmag >= kCapMinV2) {
+                const uint4 *b = tab + 2 * (size_t)cap_bin(e, vmag);
+                const uint4 in = __ldg(b);
+                rg = __ldg(b + 1);
+                a0 |= in.x; a1 |= in.y; a2 |= in.z; a3 |= in.w;
+            } else {   // (nearly) coincident centres: every point of the set takes the exact test
+                rg = make_uint4(cap_first_bits(n_points), cap_first_bits(n_points - 32), cap_first_bits(n_points - 64),
+                                cap_first_bits(n_points - 96));
+            }
+        }
+        const unsigned c0 = __reduce_or_sync(kFull, a0), c1 = __reduce_or_sync(kFull, a1),
+                       c2 = __reduce_or_sync(kFull, a2), c3 = __reduce_or_sync(kFull, a3);
+        a0 |= cap_ring<0>(rg.x & ~c0, e, pts, nbody);
+        a1 |= cap_ring<1>(rg.y & ~c1, e, pts, nbody);
+        a2 |= cap_ring<2>(rg.z & ~c2, e, pts, nbody);
+        a3 |= cap_ring<3>(rg.w & ~c3, e, pts, nbody);
+    }
+    const int covered = __popc(__reduce_or_sync(kFull, a0)) + __popc(__reduce_or_sync(kFull, a1)) +
+                        __popc(__reduce_or_sync(kFull, a2)) + __popc(__reduce_or_sync(kFull, a3));
+    return n_points - covered;
+}
+
+}  // namespace sasa

@@ -43,6 +43,7 @@ struct KParams {
     float *out_protein;
     // sphere points (SoA) and run parameters
     const float *px, *py, *pz;
+    const uint4 *cap;             // cap table of this point set (sasa_cap.cuh), n_points <= 128 only; else null
     uint32_t n_points, n_body;
     float inv_n, probe;
     float near2;                  // squared centre distance below which a neighbour is "near"

@@ -18,6 +18,7 @@
 //   phase 2  the surviving points against the remaining entries as a G x (32/G) tile of (survivor, entry) pairs
 //   tail     the n mod lanes tail points (unfused dot, <=) against all entries, same tile form
 #pragma once
+#include "sasa_cap.cuh"
 #include "sasa_small.cuh"
 
 namespace sasa {
@@ -35,6 +36,9 @@ namespace sasa {
 #ifndef SASA_OPT_TAILX
 #define SASA_OPT_TAILX 0      // tail tiles: nearest N entries tested on their own first (0: one pass over all entries).
                               // Measured (gpurun_out v1/v2, cfg2): 16 costs ~30 warp instructions per atom more than it saves.
+#endif
+#ifndef SASA_OPT_CAP
+#define SASA_OPT_CAP 1        // cap-table occlusion (sasa_cap.cuh) instead of phase 1 / tile point tests
 #endif
 #ifndef SASA_OPT_NSLT
 #define SASA_OPT_NSLT 1       // launch the kernel compiled for 3 body slots when it applies
@@ -351,6 +355,9 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                     int k = total >= 0 ? tight_gather<HAS_CLS>(V.atom, V.cls, w_list, total, pos, ai, ai.w + reach0, w_cand)
                                        : kNbCap + 1;
                     if (k <= kNbCap) {
+#if SASA_OPT_CAP
+                        cnt = cap_atom(p.cap, V.atom, ai, p.probe, w_cand, k, V.ptab, (int)p.n_points, nbody);
+#else
                         const float r = __fadd_rn(ai.w, p.probe);
                         const int nfront = tight_entries(V.atom, ai, p.probe, __fmul_rn(r, r), __fmul_rn(2.0f, r), p.near2,
                                                          w_cand, k, w_ent);
@@ -359,6 +366,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                         else if (nsl == 4) cnt = tight_atom<4>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
                         else if (nsl == 2) cnt = tight_atom<2>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
                         else cnt = tight_atom<1>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
+#endif
                         pairs += (unsigned)k;
                     } else {
                         cnt = tight_cold_atom<HAS_CLS>(p.px, p.py, p.pz, p.n_points, p.n_body, p.probe, p.near2, p.m_min, p.m_max,

@@ -15,4 +15,4 @@ import json
 d = json.load(open("$OUT/bench.json"))
 print("value %.1f M atoms/s  e2e %.1f  ms/step %.3f" % (d["value"] / 1e6, d["e2e"]["value"] / 1e6, d["ms_per_step"]))
 PY
-[ -f $OUT/tune.log ] && cat $OUT/tune.log
+if [ -f $OUT/tune.log ]; then cat $OUT/tune.log; fi
