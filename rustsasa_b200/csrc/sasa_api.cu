@@ -120,7 +120,7 @@ int get_points(sasa_b200_ctx *ctx, uint32_t n, const float **px, const uint4 **c
         CU_TRY(ctx, cudaMalloc(&P.d, h.size() * sizeof(float)));
         CU_TRY(ctx, cudaMemcpy(P.d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
         if (n <= 128) {   // the point sets of the tight kernel get their cap table (built once per context and n_points)
-            std::vector<uint32_t> t(kCapBins * 8);
+            std::vector<uint32_t> t(kCapTableBins * 8);
             cap_build_table(n, h.data(), h.data() + n, h.data() + 2 * (size_t)n, t.data());
             CU_TRY(ctx, cudaMalloc(&P.cap, t.size() * sizeof(uint32_t)));
             CU_TRY(ctx, cudaMemcpy(P.cap, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));

@@ -26,12 +26,21 @@
 #ifndef SASA_CAP_L
 #define SASA_CAP_L 64          // level bins over c in [-1, 1]
 #endif
+#ifndef SASA_CAP_RING1
+#define SASA_CAP_RING1 1       // ring tests: one loop over the lane's whole 128-bit mask (0: one loop per 32-point word)
+#endif
+#ifndef SASA_CAP_PF
+#define SASA_CAP_PF 0          // fetch the next round's masks before the current round's ring tests
+#endif
 
 namespace sasa {
 
 constexpr int kCapN = SASA_CAP_N, kCapL = SASA_CAP_L;
 constexpr int kCapLevels = kCapL + 2;                       // level 0: c < -1, level L + 1: c >= 1
 constexpr size_t kCapBins = (size_t)kCapLevels * kCapN * kCapN;
+constexpr size_t kCapBinDegenerate = kCapBins;               // extra bin: no inner points, every point in the ring
+constexpr size_t kCapBinEmpty = kCapBins + 1;                // extra bin: nothing (lanes without a neighbour)
+constexpr size_t kCapTableBins = kCapBins + 2;
 constexpr double kCapEpsAng = 1.0e-3;                        // radians added to every direction bin's radius
 constexpr double kCapEpsC = 1.0e-4;                          // widening of every level interval
 constexpr float kCapMinV2 = 1.0e-6f;                         // |v|^2 below this: no table, every point takes the exact test
@@ -53,9 +62,10 @@ inline void cap_oct_dir(double u, double v, double d[3]) {
     d[0] = x * inv; d[1] = y * inv; d[2] = z * inv;
 }
 
-inline void cap_build_table(uint32_t n, const float *px, const float *py, const float *pz, uint32_t *tab /* 8 * kCapBins */) {
+inline void cap_build_table(uint32_t n, const float *px, const float *py, const float *pz, uint32_t *tab /* 8 * kCapTableBins */) {
     const int N = kCapN, L = kCapL;
-    memset(tab, 0, kCapBins * 8 * sizeof(uint32_t));
+    memset(tab, 0, kCapTableBins * 8 * sizeof(uint32_t));
+    for (uint32_t p = 0; p < n; ++p) tab[kCapBinDegenerate * 8 + 4 + (p >> 5)] |= 1u << (p & 31);
     // level l covers c in [lo(l), hi(l)): lo(0) = -inf, lo(l) = -1 + 2 (l - 1) / L, hi(l) = lo(l + 1), hi(L + 1) = +inf
     std::vector<double> lo(kCapLevels), hi(kCapLevels);
     for (int l = 0; l < kCapLevels; ++l) {
@@ -94,52 +104,95 @@ inline void cap_build_table(uint32_t n, const float *px, const float *py, const 
 }
 
 // ---- device ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cap_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cap_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // Bin of entry e = (vx, vy, vz, limit) with vmag = |v|^2 >= kCapMinV2.  Approximate reciprocals are fine here: the bins'
 // margins absorb 1e-4 in c and 1e-3 rad in direction, these errors are ~1e-6.
 __device__ __forceinline__ int cap_bin(const float4 e, float vmag) {
-    const float c = e.w * rsqrtf(vmag);
-    const float s = __fdividef(1.0f, fabsf(e.x) + fabsf(e.y) + fabsf(e.z));
+    const float c = e.w * cap_rsqrt(vmag);
+    const float s = cap_rcp(fabsf(e.x) + fabsf(e.y) + fabsf(e.z));
     float u = e.x * s, v = e.y * s;
     if (e.z < 0.0f) {
         const float uu = copysignf(1.0f - fabsf(v), u);
         v = copysignf(1.0f - fabsf(u), v);
         u = uu;
     }
-    // __float2int_rd saturates and maps NaN to 0; the clamps make every input land in a valid bin
-    const int iu = min(max(__float2int_rd(fmaf(u, 0.5f * kCapN, 0.5f * kCapN)), 0), kCapN - 1);
-    const int iv = min(max(__float2int_rd(fmaf(v, 0.5f * kCapN, 0.5f * kCapN)), 0), kCapN - 1);
-    const int l = min(max(__float2int_rd(fmaf(c, 0.5f * kCapL, 0.5f * kCapL)) + 1, 0), kCapLevels - 1);
+    // |u|, |v| <= 1 + 1e-6: the scale just below N/2 keeps floor() inside [0, N - 1] without clamps (a direction that
+    // lands one ulp into the neighbouring bin is covered by that bin's angular margin)
+    constexpr float kHalf = 0.5f * kCapN, kScale = 0.5f * kCapN * (1.0f - 1.0f / 65536.0f);
+    const int iu = __float2int_rd(fmaf(u, kScale, kHalf));
+    const int iv = __float2int_rd(fmaf(v, kScale, kHalf));
+    // c is unbounded (and __float2int_rd saturates): level 0 below -1, level L + 1 from +1 on
+    const int l = min(max(__float2int_rd(fmaf(c, 0.5f * kCapL, 0.5f * kCapL + 1.0f)), 0), kCapLevels - 1);
     return (l * kCapN + iv) * kCapN + iu;
 }
 
-// Exact tests of this lane's neighbour e against the points of word W (points 32 W .. 32 W + 31) set in m.
-// Returns the mask of points found occluded.  MIXED: the word may hold tail points (index >= nbody: unfused dot, <=).
-template <int W, bool MIXED>
-__device__ __forceinline__ unsigned cap_ring_word(unsigned m, const float4 e, const float4 *pts, int nbody) {
-    unsigned hit = 0u;
-    while (__any_sync(kFull, m != 0u)) {
-        if (m) {
+// The reference's test of point `pt` against this lane's neighbour e (tail points: unfused dot, <=).
+__device__ __forceinline__ bool cap_exact(const float4 *pts, int pt, const float4 e, int nbody) {
+    const float4 P = pts[pt];
+    return pt >= nbody ? dot_tail(P.x, P.y, P.z, e) <= e.w : dot_body(P.x, P.y, P.z, e) < e.w;
+}
+
+// Exact tests of this lane's neighbour e against its ring points (m0..m3: points 0-31, .., 96-127 still uncovered);
+// points found occluded are OR-ed into a0..a3.
+__device__ __forceinline__ void cap_ring_tests(unsigned m0, unsigned m1, unsigned m2, unsigned m3, const float4 e,
+                                               const float4 *pts, int nbody, unsigned &a0, unsigned &a1, unsigned &a2,
+                                               unsigned &a3) {
+#if SASA_CAP_RING1
+    // every trip takes the highest point left in the lane's 128-bit mask; the warp runs max-over-lanes trips
+    while (__any_sync(kFull, (m0 | m1 | m2 | m3) != 0u)) {
+        if ((m0 | m1 | m2 | m3) != 0u) {
+            const int w = m3 ? 3 : m2 ? 2 : m1 ? 1 : 0;
+            const unsigned m = m3 ? m3 : m2 ? m2 : m1 ? m1 : m0;
             const int b = 31 - __clz(m);
             const unsigned bit = 1u << b;
-            m ^= bit;
-            const float4 P = pts[32 * W + b];
-            bool oc;
-            if (MIXED && 32 * W + b >= nbody) oc = dot_tail(P.x, P.y, P.z, e) <= e.w;
-            else oc = dot_body(P.x, P.y, P.z, e) < e.w;
-            if (oc) hit |= bit;
+            const unsigned hit = cap_exact(pts, 32 * w + b, e, nbody) ? bit : 0u;
+            if (w == 3) { m3 ^= bit; a3 |= hit; }
+            else if (w == 2) { m2 ^= bit; a2 |= hit; }
+            else if (w == 1) { m1 ^= bit; a1 |= hit; }
+            else { m0 ^= bit; a0 |= hit; }
         }
     }
-    return hit;
+#else
+    unsigned *const mm[4] = {&m0, &m1, &m2, &m3};
+    unsigned *const aa[4] = {&a0, &a1, &a2, &a3};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        unsigned m = *mm[w], hit = 0u;
+        while (__any_sync(kFull, m != 0u)) {
+            if (m) {
+                const int b = 31 - __clz(m);
+                const unsigned bit = 1u << b;
+                m ^= bit;
+                if (cap_exact(pts, 32 * w + b, e, nbody)) hit |= bit;
+            }
+        }
+        *aa[w] |= hit;
+    }
+#endif
 }
 
-template <int W>
-__device__ __forceinline__ unsigned cap_ring(unsigned m, const float4 e, const float4 *pts, int nbody) {
-    if (32 * W + 32 <= nbody) return cap_ring_word<W, false>(m, e, pts, nbody);
-    return cap_ring_word<W, true>(m, e, pts, nbody);
-}
+struct CapRound {
+    float4 e;       // this lane's neighbour: (vx, vy, vz, limit), the reference's arithmetic
+    uint4 in, rg;   // its bin's inner and ring masks
+};
 
-// The first min(max(n, 0), 32) bits set.
-__device__ __forceinline__ unsigned cap_first_bits(int n) { return n <= 0 ? 0u : n >= 32 ? 0xffffffffu : (1u << n) - 1u; }
+// Lane `lane` of the round starting at q0: entry + table fetch (lanes past k fetch the empty bin).
+__device__ __forceinline__ CapRound cap_fetch(const uint4 *__restrict__ tab, const float4 *s_atom, const float4 ai, float probe,
+                                              float r2, float two_r, const uint16_t *cand, int q, int k) {
+    CapRound R;
+    const bool valid = q < k;
+    const float4 aj = s_atom[valid ? (int)cand[q] : 0];
+    float vmag;
+    R.e = make_entry(ai, aj, probe, r2, two_r, &vmag);
+    // (nearly) coincident centres: no direction -- the degenerate bin sends every point to the exact test
+    const int bin = valid ? (vmag >= kCapMinV2 ? cap_bin(R.e, vmag) : (int)kCapBinDegenerate) : (int)kCapBinEmpty;
+    const uint4 *b = tab + 2 * (size_t)(unsigned)bin;
+    R.in = __ldg(b);
+    R.rg = __ldg(b + 1);
+    return R;
+}
 
 // One atom: neighbours cand[0, k) (positions in the cell-sorted shared atom array).  Returns the exposed-point count.
 // Lane q of round r owns neighbour 32 r + q: it builds the entry with the reference's arithmetic (make_entry), fetches
@@ -151,31 +204,24 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const flo
     const float r = __fadd_rn(ai.w, probe);
     const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
     unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;      // this lane's inner masks and exact hits, not yet reduced
+#if SASA_CAP_PF
+    CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, lane, k);
 #pragma unroll 1
     for (int q0 = 0; q0 < k; q0 += 32) {
-        const int q = q0 + lane;
-        const bool valid = q < k;
-        const float4 aj = s_atom[valid ? (int)cand[q] : 0];
-        float vmag;
-        const float4 e = make_entry(ai, aj, probe, r2, two_r, &vmag);
-        uint4 rg = make_uint4(0u, 0u, 0u, 0u);
-        if (valid) {
-            if (vmag >= kCapMinV2) {
-                const uint4 *b = tab + 2 * (size_t)cap_bin(e, vmag);
-                const uint4 in = __ldg(b);
-                rg = __ldg(b + 1);
-                a0 |= in.x; a1 |= in.y; a2 |= in.z; a3 |= in.w;
-            } else {   // (nearly) coincident centres: every point of the set takes the exact test
-                rg = make_uint4(cap_first_bits(n_points), cap_first_bits(n_points - 32), cap_first_bits(n_points - 64),
-                                cap_first_bits(n_points - 96));
-            }
-        }
+        CapRound Nx = R;
+        if (q0 + 32 < k) Nx = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, q0 + 32 + lane, k);
+#else
+#pragma unroll 1
+    for (int q0 = 0; q0 < k; q0 += 32) {
+        const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, q0 + lane, k);
+#endif
+        a0 |= R.in.x; a1 |= R.in.y; a2 |= R.in.z; a3 |= R.in.w;
         const unsigned c0 = __reduce_or_sync(kFull, a0), c1 = __reduce_or_sync(kFull, a1),
                        c2 = __reduce_or_sync(kFull, a2), c3 = __reduce_or_sync(kFull, a3);
-        a0 |= cap_ring<0>(rg.x & ~c0, e, pts, nbody);
-        a1 |= cap_ring<1>(rg.y & ~c1, e, pts, nbody);
-        a2 |= cap_ring<2>(rg.z & ~c2, e, pts, nbody);
-        a3 |= cap_ring<3>(rg.w & ~c3, e, pts, nbody);
+        cap_ring_tests(R.rg.x & ~c0, R.rg.y & ~c1, R.rg.z & ~c2, R.rg.w & ~c3, R.e, pts, nbody, a0, a1, a2, a3);
+#if SASA_CAP_PF
+        R = Nx;
+#endif
     }
     const int covered = __popc(__reduce_or_sync(kFull, a0)) + __popc(__reduce_or_sync(kFull, a1)) +
                         __popc(__reduce_or_sync(kFull, a2)) + __popc(__reduce_or_sync(kFull, a3));

@@ -22,7 +22,7 @@ def func_ranges(path):
 def main():
     dump, want = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
     ranges = {}
-    for f in ("sasa_device.cuh", "sasa_small.cuh", "sasa_tight.cuh", "sasa_large.cuh"):
+    for f in ("sasa_device.cuh", "sasa_small.cuh", "sasa_tight.cuh", "sasa_large.cuh", "sasa_cap.cuh"):
         ranges[f] = func_ranges(os.path.join(ROOT, "rustsasa_b200", "csrc", f))
     rows = list(csv.reader(open(dump)))
     cur_file = cur_fn = hdr = None
