@@ -21,7 +21,7 @@
 #include "sasa_device.cuh"
 
 #ifndef SASA_CAP_N
-#define SASA_CAP_N 64          // direction bins per axis of the octahedral square (even)
+#define SASA_CAP_N 128         // direction bins per axis of the octahedral square (even)
 #endif
 #ifndef SASA_CAP_L
 #define SASA_CAP_L 64          // level bins over c in [-1, 1]

@@ -252,17 +252,23 @@ __device__ __forceinline__ bool structure_setup(const KParams &p, const SmemView
 
 // Per-atom counts -> areas (coalesced stores), then the level sums in the reference's order: replaces the
 // numeric part of process_atoms (src/options.rs:195-232, :292-315, :370-410) and simd_sum (src/utils.rs:14-22).
-template <int NT>
+// AREA_READY: val already holds areas and the counts have been written (tight kernel).
+template <int NT, bool AREA_READY = false>
 __device__ __forceinline__ void structure_outputs(const KParams &p, const SmemView &V, uint32_t sid, uint32_t a0, int N) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < N; i += NT) {
-        const float cnt = V.val[i];
-        const float area = atom_area(p.xyz3 ? __ldg(p.radii + i) : __ldg(p.xyzr + a0 + i).w, p.probe, cnt, p.inv_n);
-        if (p.out_counts) p.out_counts[a0 + i] = (uint32_t)cnt;
-        if (p.out_atom) p.out_atom[a0 + i] = area;
-        V.val[i] = area;
+    if (AREA_READY) {
+        if (p.out_atom)
+            for (int i = tid; i < N; i += NT) p.out_atom[a0 + i] = V.val[i];
+    } else {
+        for (int i = tid; i < N; i += NT) {
+            const float cnt = V.val[i];
+            const float area = atom_area(p.xyz3 ? __ldg(p.radii + i) : __ldg(p.xyzr + a0 + i).w, p.probe, cnt, p.inv_n);
+            if (p.out_counts) p.out_counts[a0 + i] = (uint32_t)cnt;
+            if (p.out_atom) p.out_atom[a0 + i] = area;
+            V.val[i] = area;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (p.seg_be) {
         const uint32_t g0 = p.struct_seg_off[sid], g1 = p.struct_seg_off[sid + 1];
         if (p.out_seg) {
@@ -307,6 +313,42 @@ __device__ __forceinline__ bool claim_structure(const KParams &p, int *misc, uin
     a0 = p.struct_off[sid];
     N = (int)(p.struct_off[sid + 1] - a0);
     return true;
+}
+
+// The same with the claim taken early: warp 0 of the CTA calls claim_next_and_prefetch while the other warps already
+// work on the current structure -- it takes the next queue position, reads that structure's range into misc[2..5] and
+// prefetches its atoms into L2, so that
+// neither the atomic's round trip nor the first touch of the input sits on the CTA's critical path.
+__device__ __forceinline__ void claim_next_and_prefetch(const KParams &p, int *misc) {
+    const int lane = lane_id();
+    uint32_t na0 = 0, nN = 0;
+    if (lane == 0) {
+        const uint32_t w = atomicAdd(p.work_counter, 1u);
+        uint32_t nsid = 0;
+        if (w < p.n_work) {
+            nsid = p.order[w];
+            na0 = p.struct_off[nsid];
+            nN = p.struct_off[nsid + 1] - na0;
+        }
+        misc[2] = (int)(w < p.n_work);
+        misc[3] = (int)nsid;
+        misc[4] = (int)na0;
+        misc[5] = (int)nN;
+    }
+    na0 = __shfl_sync(kFull, na0, 0);
+    nN = __shfl_sync(kFull, nN, 0);
+    const char *base = p.xyz3 ? reinterpret_cast<const char *>(p.xyz3 + 3 * (size_t)na0) : reinterpret_cast<const char *>(p.xyzr + na0);
+    const size_t bytes = (size_t)nN * (p.xyz3 ? 12 : 16);
+    for (size_t o = (size_t)lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+}
+
+__device__ __forceinline__ bool claim_prefetched(int *misc, uint32_t &sid, uint32_t &a0, int &N) {
+    __syncthreads();
+    const int have = misc[2];
+    sid = (uint32_t)misc[3];
+    a0 = (uint32_t)misc[4];
+    N = misc[5];
+    return have != 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -43,6 +43,21 @@ namespace sasa {
 #ifndef SASA_OPT_NSLT
 #define SASA_OPT_NSLT 1       // launch the kernel compiled for 3 body slots when it applies
 #endif
+#ifndef SASA_OPT_GU
+#define SASA_OPT_GU 2         // gather: 32-candidate steps per unrolled trip
+#endif
+#ifndef SASA_OPT_AREA
+#define SASA_OPT_AREA 0       // the per-atom phase stores areas (and writes counts straight to global memory): the output
+                              // stage needs no second read of the radii
+#endif
+#ifndef SASA_OPT_ACLAIM
+#define SASA_OPT_ACLAIM 4     // > 0: warps claim runs of ATOMS (at least this many) of the cell-sorted order instead of runs
+                              // of cells -- finer tail at the price of some cells' candidate lists being built twice
+#endif
+#ifndef SASA_OPT_NEXT
+#define SASA_OPT_NEXT 1       // warp 0 claims the CTA's next structure and prefetches its atoms into L2 while the other
+                              // warps already work on the current one (hides the claim / first-touch latency of the setup)
+#endif
 
 // Flatten the candidate rows of cell (cx, cy, cz) into list[0, total) (positions in the sorted atom array),
 // padded with `sentinel` up to the next multiple of 32.  Returns total, or -1 when it exceeds kListCap.
@@ -102,7 +117,8 @@ __device__ __forceinline__ int tight_gather(const float4 *s_atom, const uint32_t
     const unsigned lt = lanemask_lt();
     const uint32_t cls_i = HAS_CLS ? s_cls[pos] : 0u;
     int k = 0;
-#pragma unroll 2
+    constexpr int kGU = SASA_OPT_GU;
+#pragma unroll kGU
     for (int w0 = 0; w0 < total; w0 += 32) {
         const int j = (int)list[w0 + lane];
         const float4 aj = s_atom[j];
@@ -320,10 +336,20 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
 
     uint32_t sid, a0;
     int N;
+#if SASA_OPT_NEXT
+    bool first = true;
+    while (first ? claim_structure(p, V.misc, sid, a0, N) : claim_prefetched(V.misc, sid, a0, N)) {
+        first = false;
+#else
     while (claim_structure(p, V.misc, sid, a0, N)) {
+#endif
         Grid g;
         int ncell;
-        if (!structure_setup<NT, HAS_CLS, CMAX>(p, V, sid, a0, N, g, ncell)) continue;
+        const bool ok = structure_setup<NT, HAS_CLS, CMAX>(p, V, sid, a0, N, g, ncell);
+#if SASA_OPT_NEXT
+        if (warp == 0) claim_next_and_prefetch(p, V.misc);   // every structure, also after a rejected one
+#endif
+        if (!ok) continue;
 
         // ---- per-atom work: warps claim runs of consecutive cells; the atoms of a cell share its candidate list ----
         unsigned pairs = 0, streamed = 0;
@@ -331,6 +357,18 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
             // guided self-scheduling: long runs of cells while plenty remain, short ones near the end of the structure
             // (any positive increment partitions the cells, so the stale read of the counter is harmless)
             int c0 = 0, take = 0;
+#if SASA_OPT_ACLAIM > 0
+            if (lane == 0) {
+                const int left = N - *(volatile int *)&V.misc[1];
+                take = max(SASA_OPT_ACLAIM, min(16 * SASA_OPT_ACLAIM, left / (4 * NW)));
+                c0 = atomicAdd(&V.misc[1], take);
+            }
+            c0 = __shfl_sync(kFull, c0, 0);
+            take = __shfl_sync(kFull, take, 0);
+            if (c0 >= N) break;
+            int pos = c0;
+            const int pos_end = min(c0 + take, N);
+#else
             if (lane == 0) {
                 const int left = ncell - *(volatile int *)&V.misc[1];
                 take = max(SASA_CELL_FETCH, min(8 * SASA_CELL_FETCH, left / (4 * NW)));
@@ -342,12 +380,13 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
             const int c1 = min(c0 + take, ncell);
             int pos = (int)V.cell[c0];
             const int pos_end = (int)V.cell[c1];
+#endif
             while (pos < pos_end) {
                 // the cell of atom `pos` and the end of its run in the sorted array
                 const float4 a_first = V.atom[pos];
                 const int cx = cell_coord(a_first.x, g.minx, g.inv_c, g.nx), cy = cell_coord(a_first.y, g.miny, g.inv_c, g.ny),
                           cz = cell_coord(a_first.z, g.minz, g.inv_c, g.nz);
-                const int cell_end = (int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1];
+                const int cell_end = min((int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1], pos_end);
                 const int total = tight_fill_list(g, V.cell, cx, cy, cz, w_list, N);
                 for (; pos < cell_end; ++pos) {
                     const float4 ai = V.atom[pos];
@@ -372,7 +411,15 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                         cnt = tight_cold_atom<HAS_CLS>(p.px, p.py, p.pz, p.n_points, p.n_body, p.probe, p.near2, p.m_min, p.m_max,
                                                        g, V.atom, V.cell, V.cls, V.ptab, pos, w_ent, w_cand, &pairs, &streamed);
                     }
-                    if (lane == 0) V.val[V.orig[pos]] = (float)cnt;
+                    if (lane == 0) {
+                        const int oi = (int)V.orig[pos];
+#if SASA_OPT_AREA
+                        V.val[oi] = atom_area(ai.w, p.probe, (float)cnt, p.inv_n);
+                        if (p.out_counts) p.out_counts[a0 + oi] = (uint32_t)cnt;
+#else
+                        V.val[oi] = (float)cnt;
+#endif
+                    }
                     __syncwarp();
                 }
             }
@@ -382,7 +429,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
             if (streamed) atomicAdd(p.stat + 2, (unsigned long long)streamed);
         }
         __syncthreads();
-        structure_outputs<NT>(p, V, sid, a0, N);
+        structure_outputs<NT, SASA_OPT_AREA != 0>(p, V, sid, a0, N);
     }
 }
 
