@@ -29,6 +29,10 @@
 #ifndef SASA_CAP_RING1
 #define SASA_CAP_RING1 1       // ring tests: one loop over the lane's whole 128-bit mask (0: one loop per 32-point word)
 #endif
+#ifndef SASA_CAP_R2
+#define SASA_CAP_R2 1          // rounds 0 and 1 (the first 64 neighbours) are fetched together: one OR-reduction for both, the
+                               // ring tests of round 0 already see the inner masks of round 1, and both fetches overlap
+#endif
 #ifndef SASA_CAP_PF
 #define SASA_CAP_PF 0          // fetch the next round's masks before the current round's ring tests
 #endif
@@ -194,6 +198,20 @@ __device__ __forceinline__ CapRound cap_fetch(const uint4 *__restrict__ tab, con
     return R;
 }
 
+// One round of an atom, given this lane's entry and masks: OR of the inner masks, exact tests of the ring points left.
+__device__ __forceinline__ void cap_round(const CapRound &R, const float4 *pts, int nbody, unsigned &a0, unsigned &a1, unsigned &a2,
+                                          unsigned &a3) {
+    a0 |= R.in.x; a1 |= R.in.y; a2 |= R.in.z; a3 |= R.in.w;
+    const unsigned c0 = __reduce_or_sync(kFull, a0), c1 = __reduce_or_sync(kFull, a1),
+                   c2 = __reduce_or_sync(kFull, a2), c3 = __reduce_or_sync(kFull, a3);
+    cap_ring_tests(R.rg.x & ~c0, R.rg.y & ~c1, R.rg.z & ~c2, R.rg.w & ~c3, R.e, pts, nbody, a0, a1, a2, a3);
+}
+
+__device__ __forceinline__ int cap_covered(unsigned a0, unsigned a1, unsigned a2, unsigned a3) {
+    return __popc(__reduce_or_sync(kFull, a0)) + __popc(__reduce_or_sync(kFull, a1)) +
+           __popc(__reduce_or_sync(kFull, a2)) + __popc(__reduce_or_sync(kFull, a3));
+}
+
 // One atom: neighbours cand[0, k) (positions in the cell-sorted shared atom array).  Returns the exposed-point count.
 // Lane q of round r owns neighbour 32 r + q: it builds the entry with the reference's arithmetic (make_entry), fetches
 // its bin's masks, and -- after the warp-wide OR of the inner masks -- runs the exact test on its own ring points that
@@ -204,28 +222,91 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const flo
     const float r = __fadd_rn(ai.w, probe);
     const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
     unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;      // this lane's inner masks and exact hits, not yet reduced
-#if SASA_CAP_PF
+#if SASA_CAP_R2
+    {
+        const CapRound A = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, lane, k);
+        CapRound B;
+        B.e = make_float4(0.f, 0.f, 0.f, 0.f);
+        B.in = make_uint4(0u, 0u, 0u, 0u);
+        B.rg = B.in;
+        if (k > 32) B = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, 32 + lane, k);
+        a0 = A.in.x | B.in.x; a1 = A.in.y | B.in.y; a2 = A.in.z | B.in.z; a3 = A.in.w | B.in.w;
+        const unsigned c0 = __reduce_or_sync(kFull, a0), c1 = __reduce_or_sync(kFull, a1),
+                       c2 = __reduce_or_sync(kFull, a2), c3 = __reduce_or_sync(kFull, a3);
+        cap_ring_tests(A.rg.x & ~c0, A.rg.y & ~c1, A.rg.z & ~c2, A.rg.w & ~c3, A.e, pts, nbody, a0, a1, a2, a3);
+        if (k > 32) cap_ring_tests(B.rg.x & ~c0, B.rg.y & ~c1, B.rg.z & ~c2, B.rg.w & ~c3, B.e, pts, nbody, a0, a1, a2, a3);
+    }
+#pragma unroll 1
+    for (int q0 = 64; q0 < k; q0 += 32) {
+        const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, q0 + lane, k);
+        cap_round(R, pts, nbody, a0, a1, a2, a3);
+    }
+#elif SASA_CAP_PF
     CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, lane, k);
 #pragma unroll 1
     for (int q0 = 0; q0 < k; q0 += 32) {
         CapRound Nx = R;
         if (q0 + 32 < k) Nx = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, q0 + 32 + lane, k);
+        cap_round(R, pts, nbody, a0, a1, a2, a3);
+        R = Nx;
+    }
 #else
 #pragma unroll 1
     for (int q0 = 0; q0 < k; q0 += 32) {
         const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, q0 + lane, k);
-#endif
-        a0 |= R.in.x; a1 |= R.in.y; a2 |= R.in.z; a3 |= R.in.w;
-        const unsigned c0 = __reduce_or_sync(kFull, a0), c1 = __reduce_or_sync(kFull, a1),
-                       c2 = __reduce_or_sync(kFull, a2), c3 = __reduce_or_sync(kFull, a3);
-        cap_ring_tests(R.rg.x & ~c0, R.rg.y & ~c1, R.rg.z & ~c2, R.rg.w & ~c3, R.e, pts, nbody, a0, a1, a2, a3);
-#if SASA_CAP_PF
-        R = Nx;
-#endif
+        cap_round(R, pts, nbody, a0, a1, a2, a3);
     }
-    const int covered = __popc(__reduce_or_sync(kFull, a0)) + __popc(__reduce_or_sync(kFull, a1)) +
-                        __popc(__reduce_or_sync(kFull, a2)) + __popc(__reduce_or_sync(kFull, a3));
-    return n_points - covered;
+#endif
+    return n_points - cap_covered(a0, a1, a2, a3);
+}
+
+// ---- the same, split in two so that the table latency of an atom's first round hides behind the neighbour search of the
+// next atom: cap_issue builds the entries of round 0, parks them in the warp's staging area and starts the asynchronous
+// copy (LDGSTS, no registers in flight) of their bins' masks into it; cap_finish waits for the copy and does the rest.
+// Staging layout (kCapStageBytes per warp): float4 e[32] | uint4 inner[32] | uint4 ring[32].
+constexpr int kCapStageBytes = 96 * 16;
+
+__device__ __forceinline__ void cap_issue(const uint4 *__restrict__ tab, const float4 *s_atom, const float4 ai, float probe,
+                                          const uint16_t *cand, int k, float4 *stage) {
+    const int lane = lane_id();
+    const float r = __fadd_rn(ai.w, probe);
+    const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
+    const bool valid = lane < k;
+    const float4 aj = s_atom[valid ? (int)cand[lane] : 0];
+    float vmag;
+    const float4 e = make_entry(ai, aj, probe, r2, two_r, &vmag);
+    const int bin = valid ? (vmag >= kCapMinV2 ? cap_bin(e, vmag) : (int)kCapBinDegenerate) : (int)kCapBinEmpty;
+    stage[lane] = e;
+    const uint4 *b = tab + 2 * (size_t)(unsigned)bin;
+    const unsigned d_in = (unsigned)__cvta_generic_to_shared(stage + 32 + lane);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d_in), "l"(b));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d_in + 32 * 16), "l"(b + 1));
+    asm volatile("cp.async.commit_group;");
+}
+
+__device__ __forceinline__ int cap_finish(const uint4 *__restrict__ tab, const float4 *s_atom, const float4 ai, float probe,
+                                          const uint16_t *cand, int k, const float4 *pts, int n_points, int nbody,
+                                          const float4 *stage) {
+    const int lane = lane_id();
+    unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    {
+        CapRound R;     // every lane reads back what it staged itself
+        R.e = stage[lane];
+        R.in = reinterpret_cast<const uint4 *>(stage)[32 + lane];
+        R.rg = reinterpret_cast<const uint4 *>(stage)[64 + lane];
+        cap_round(R, pts, nbody, a0, a1, a2, a3);
+    }
+    if (k > 32) {
+        const float r = __fadd_rn(ai.w, probe);
+        const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
+#pragma unroll 1
+        for (int q0 = 32; q0 < k; q0 += 32) {
+            const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, q0 + lane, k);
+            cap_round(R, pts, nbody, a0, a1, a2, a3);
+        }
+    }
+    return n_points - cap_covered(a0, a1, a2, a3);
 }
 
 }  // namespace sasa

@@ -33,7 +33,7 @@ struct SmallLayout {
 };
 
 __host__ __device__ constexpr size_t small_fixed_bytes(int nwarps) {
-    return 128 * 16 + (size_t)nwarps * kNbCap * 16 + (size_t)nwarps * kQueueCap * 2 + (size_t)nwarps * kListCap * 2 +
+    return 128 * 16 + (size_t)nwarps * kNbCap * 16 + (size_t)nwarps * kCandSlots * 2 + (size_t)nwarps * kListCap * 2 +
            32 * 8 * 4 + 64;
 }
 
@@ -42,7 +42,7 @@ __host__ __device__ constexpr SmallLayout small_layout(uint32_t nmax, uint32_t c
     size_t o = 0;
     L.pts = o;   o += 128 * 16;
     L.ent = o;   o += (size_t)nwarps * kNbCap * 16;
-    L.cand = o;  o += (size_t)nwarps * kQueueCap * 2;
+    L.cand = o;  o += (size_t)nwarps * kCandSlots * 2;
     L.list = o;  o += (size_t)nwarps * kListCap * 2;
     L.red = o;   o += 32 * 8 * 4;
     L.misc = o;  o += 64;
@@ -110,7 +110,8 @@ struct SmemView {
     float4 *ptab;       // 128 sphere points as float4 (n_points <= 128), else unused
     float4 *atom;       // cell-sorted atoms; atom[N] is the far-away sentinel of the tight kernel
     float *red;         // block reduction scratch
-    int *misc;          // [0] structure claimed by the CTA, [1] work counter of the per-atom loop
+    int *misc;          // [0] structure claimed by the CTA, [1] work counter of the per-atom loop, [2..5] the next structure
+                        // (claim_next_and_prefetch), [6..7] statistics, [8..15] the cell grid (store_grid / load_grid)
     float *val;         // per-atom exposed-point count, then area, by ORIGINAL index
     uint16_t *cellid, *rank;   // alias val during the counting sort
     uint32_t *cls;      // id classes in sorted order (HAS_CLS)
@@ -145,6 +146,20 @@ __device__ __forceinline__ void stage_points(const KParams &p, float4 *ptab) {
         const bool v = (uint32_t)t < p.n_points;
         ptab[t] = make_float4(v ? __ldg(p.px + t) : 0.f, v ? __ldg(p.py + t) : 0.f, v ? __ldg(p.pz + t) : 0.f, 0.f);
     }
+}
+
+// The structure's cell grid parked in misc[8..15]: the tight kernel re-reads it at every cell instead of keeping it in
+// registers (volatile: the loads must stay where they are written).
+__device__ __forceinline__ void store_grid(int *misc, const Grid &g) {
+    misc[8] = __float_as_int(g.minx); misc[9] = __float_as_int(g.miny); misc[10] = __float_as_int(g.minz);
+    misc[11] = __float_as_int(g.inv_c); misc[12] = g.nx; misc[13] = g.ny; misc[14] = g.nz; misc[15] = g.e;
+}
+__device__ __forceinline__ Grid load_grid(const int *misc) {
+    const volatile int *m = misc;
+    Grid g;
+    g.minx = __int_as_float(m[8]); g.miny = __int_as_float(m[9]); g.minz = __int_as_float(m[10]);
+    g.inv_c = __int_as_float(m[11]); g.nx = m[12]; g.ny = m[13]; g.nz = m[14]; g.e = m[15];
+    return g;
 }
 
 // One structure from raw float4 atoms to a cell-sorted shared-memory copy: bounds / r_max / finiteness (one fused
@@ -244,6 +259,9 @@ __device__ __forceinline__ bool structure_setup(const KParams &p, const SmemView
     }
     if (tid == 0) {
         V.misc[1] = 0;
+        V.misc[6] = 0;   // neighbour pairs / streamed atoms of this structure (tight kernel)
+        V.misc[7] = 0;
+        store_grid(V.misc, g);
         V.atom[N] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.0f);   // sentinel: farther than any cutoff from everything
     }
     __syncthreads();   // cellid / rank are dead from here on: val may be written
@@ -363,7 +381,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
     const SmemView V = smem_view<NT, HAS_CLS, NMAX, CMAX>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *const w_ent = reinterpret_cast<float4 *>(smem + kOffEnt) + warp * kNbCap;
-    uint16_t *const w_cand = reinterpret_cast<uint16_t *>(smem + kOffCand) + warp * kQueueCap;
+    uint16_t *const w_cand = reinterpret_cast<uint16_t *>(smem + kOffCand) + warp * kCandSlots;
     const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0;
     const float4 *s_pts = p.n_points <= 128 ? V.ptab : nullptr;
     stage_points(p, V.ptab);

@@ -54,6 +54,10 @@ namespace sasa {
 #define SASA_OPT_ACLAIM 4     // > 0: warps claim runs of ATOMS (at least this many) of the cell-sorted order instead of runs
                               // of cells -- finer tail at the price of some cells' candidate lists being built twice
 #endif
+#ifndef SASA_OPT_PIPE
+#define SASA_OPT_PIPE 0       // cap path: an atom's first table round is fetched asynchronously (LDGSTS into the warp's staging
+                              // area) and consumed after the NEXT atom's neighbour search
+#endif
 #ifndef SASA_OPT_NEXT
 #define SASA_OPT_NEXT 1       // warp 0 claims the CTA's next structure and prefetches its atoms into L2 while the other
                               // warps already work on the current one (hides the claim / first-touch latency of the setup)
@@ -291,12 +295,12 @@ __device__ __forceinline__ int tight_atom(const KParams &p, const float4 *ent, i
 // Cold path, out of line on purpose.  Cells with more than kListCap candidates (structures whose bounding box
 // forced a coarser grid) take the generic per-atom gather and the generic chunked evaluation; atoms with more
 // than kNbCap neighbours (denser than any protein) the list-free streaming routine.  Returns the exposed-point
-// count and adds the atom's list length to *pairs, or 1 to *streamed.
+// count and adds the atom's list length to misc[6] (pairs), or 1 to misc[7] (streamed atoms).
 template <bool HAS_CLS>
 __device__ __noinline__ int tight_cold_atom(const float *px, const float *py, const float *pz, uint32_t n_points, uint32_t n_body,
                                             float probe, float near2, int m_min, int m_max, Grid g, const float4 *s_atom,
                                             const uint16_t *s_cell, const uint32_t *s_cls, const float4 *s_pts, int pos,
-                                            float4 *ent, uint16_t *cand, unsigned *pairs, unsigned *streamed) {
+                                            float4 *ent, uint16_t *cand, int *misc) {
     KParams q;
     q.px = px; q.py = py; q.pz = pz;
     q.n_points = n_points; q.n_body = n_body; q.probe = probe;
@@ -308,10 +312,10 @@ __device__ __noinline__ int tight_cold_atom(const float *px, const float *py, co
     if (k >= 0) {
         const float r = __fadd_rn(ai.w, probe);
         const int nfront = build_entries(q, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), cand, k, ent);
-        *pairs += (unsigned)k;
+        if (lane_id() == 0) atomicAdd(&misc[6], k);
         return (int)atom_fast(q, ent, k, nfront, cand, s_pts);
     }
-    *streamed += 1;
+    if (lane_id() == 0) atomicAdd(&misc[7], 1);
     return (int)atom_streaming<SmemAtoms, uint16_t, false>(q, g, atoms, s_cell, cls, pos, ent, nullptr);
 }
 
@@ -323,11 +327,11 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
     constexpr int NW = NT / 32;
     constexpr uint32_t NMAX = max_atoms(NT, MINB, CMAX, HAS_CLS);
     constexpr size_t kOffEnt = 128 * 16, kOffCand = kOffEnt + (size_t)NW * kNbCap * 16,
-                     kOffList = kOffCand + (size_t)NW * kQueueCap * 2;
+                     kOffList = kOffCand + (size_t)NW * kCandSlots * 2;
     const SmemView V = smem_view<NT, HAS_CLS, NMAX, CMAX>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 *const w_ent = reinterpret_cast<float4 *>(smem + kOffEnt) + warp * kNbCap;
-    uint16_t *const w_cand = reinterpret_cast<uint16_t *>(smem + kOffCand) + warp * kQueueCap;
+    uint16_t *const w_cand = reinterpret_cast<uint16_t *>(smem + kOffCand) + warp * kCandSlots;
     uint16_t *const w_list = reinterpret_cast<uint16_t *>(smem + kOffList) + warp * kListCap;
     stage_points(p, V.ptab);
     const int nbody = (int)min(p.n_points, p.n_body), nsl = (nbody + 31) >> 5;
@@ -352,7 +356,6 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
         if (!ok) continue;
 
         // ---- per-atom work: warps claim runs of consecutive cells; the atoms of a cell share its candidate list ----
-        unsigned pairs = 0, streamed = 0;
         for (;;) {
             // guided self-scheduling: long runs of cells while plenty remain, short ones near the end of the structure
             // (any positive increment partitions the cells, so the stale read of the counter is harmless)
@@ -381,6 +384,53 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
             int pos = (int)V.cell[c0];
             const int pos_end = (int)V.cell[c1];
 #endif
+#if SASA_OPT_CAP && SASA_OPT_PIPE
+            // software pipeline over the atoms of the run, one flat loop (a single inlined copy of every stage):
+            //   gather(i) | finish(i - 1) | issue(i)      -- the table masks of atom i are in flight during gather(i + 1)
+            // st = the atom in flight: pos | k << 16 | candidate buffer << 24, or -1
+            int st = -1, cell_end = pos, total = 0;
+            for (;;) {
+                const bool have = pos < pos_end;
+                const int cb = st >= 0 ? ((st >> 24) ^ 1) : 0;
+                int k = 0;
+                if (have) {
+                    const float4 ai = V.atom[pos];
+                    if (pos >= cell_end) {   // first atom of a cell: its candidate list (the grid is re-read from shared
+                        const Grid g = load_grid(V.misc);   // memory here instead of pinning 8 registers through the loop)
+                        const int cx = cell_coord(ai.x, g.minx, g.inv_c, g.nx), cy = cell_coord(ai.y, g.miny, g.inv_c, g.ny),
+                                  cz = cell_coord(ai.z, g.minz, g.inv_c, g.nz);
+                        cell_end = min((int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1], pos_end);
+                        total = tight_fill_list(g, V.cell, cx, cy, cz, w_list, N);
+                    }
+                    k = total >= 0 ? tight_gather<HAS_CLS>(V.atom, V.cls, w_list, total, pos, ai, ai.w + reach0, w_cand + cb * kQueueCap)
+                                   : kNbCap + 1;
+                }
+                if (st >= 0) {
+                    const int ppos = st & 0xffff;
+                    const int cnt = cap_finish(p.cap, V.atom, V.atom[ppos], p.probe, w_cand + (cb ^ 1) * kQueueCap, (st >> 16) & 0xff,
+                                               V.ptab, (int)p.n_points, nbody, w_ent);
+                    if (lane == 0) {
+                        V.val[V.orig[ppos]] = (float)cnt;
+                        atomicAdd(&V.misc[6], (st >> 16) & 0xff);
+                    }
+                    st = -1;
+                    __syncwarp();
+                }
+                if (!have) break;
+                if (k <= kNbCap) {
+                    cap_issue(p.cap, V.atom, V.atom[pos], p.probe, w_cand + cb * kQueueCap, k, w_ent);
+                    st = pos | (k << 16) | (cb << 24);
+                } else {
+                    const int cnt = tight_cold_atom<HAS_CLS>(p.px, p.py, p.pz, p.n_points, p.n_body, p.probe, p.near2, p.m_min,
+                                                             p.m_max, load_grid(V.misc), V.atom, V.cell, V.cls, V.ptab, pos, w_ent,
+                                                             w_cand + cb * kQueueCap, V.misc);
+                    if (lane == 0) V.val[V.orig[pos]] = (float)cnt;
+                    __syncwarp();
+                }
+                ++pos;
+            }
+        }
+#else
             while (pos < pos_end) {
                 // the cell of atom `pos` and the end of its run in the sorted array
                 const float4 a_first = V.atom[pos];
@@ -406,10 +456,10 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                         else if (nsl == 2) cnt = tight_atom<2>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
                         else cnt = tight_atom<1>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
 #endif
-                        pairs += (unsigned)k;
+                        if (lane == 0) atomicAdd(&V.misc[6], k);
                     } else {
                         cnt = tight_cold_atom<HAS_CLS>(p.px, p.py, p.pz, p.n_points, p.n_body, p.probe, p.near2, p.m_min, p.m_max,
-                                                       g, V.atom, V.cell, V.cls, V.ptab, pos, w_ent, w_cand, &pairs, &streamed);
+                                                       g, V.atom, V.cell, V.cls, V.ptab, pos, w_ent, w_cand, V.misc);
                     }
                     if (lane == 0) {
                         const int oi = (int)V.orig[pos];
@@ -424,11 +474,12 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                 }
             }
         }
-        if (lane == 0 && p.stat) {
-            if (pairs) atomicAdd(p.stat + 1, (unsigned long long)pairs);
-            if (streamed) atomicAdd(p.stat + 2, (unsigned long long)streamed);
-        }
+#endif
         __syncthreads();
+        if (threadIdx.x == 0 && p.stat) {
+            if (V.misc[6]) atomicAdd(p.stat + 1, (unsigned long long)(unsigned)V.misc[6]);
+            if (V.misc[7]) atomicAdd(p.stat + 2, (unsigned long long)(unsigned)V.misc[7]);
+        }
         structure_outputs<NT, SASA_OPT_AREA != 0>(p, V, sid, a0, N);
     }
 }
