@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
         if (!ok) continue;
 
         // ---- per-atom work: warps claim runs of consecutive cells; the atoms of a cell share its candidate list ----
+        unsigned pairs = 0;   // neighbour pairs seen by this warp (statistics; the cold path counts into misc[6] itself)
         for (;;) {
             // guided self-scheduling: long runs of cells while plenty remain, short ones near the end of the structure
             // (any positive increment partitions the cells, so the stale read of the counter is harmless)
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                         else if (nsl == 2) cnt = tight_atom<2>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
                         else cnt = tight_atom<1>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
 #endif
-                        if (lane == 0) atomicAdd(&V.misc[6], k);
+                        pairs += (unsigned)k;
                     } else {
                         cnt = tight_cold_atom<HAS_CLS>(p.px, p.py, p.pz, p.n_points, p.n_body, p.probe, p.near2, p.m_min, p.m_max,
                                                        g, V.atom, V.cell, V.cls, V.ptab, pos, w_ent, w_cand, V.misc);
@@ -475,6 +476,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
             }
         }
 #endif
+        if (lane == 0 && pairs) atomicAdd(&V.misc[6], (int)pairs);
         __syncthreads();
         if (threadIdx.x == 0 && p.stat) {
             if (V.misc[6]) atomicAdd(p.stat + 1, (unsigned long long)(unsigned)V.misc[6]);
