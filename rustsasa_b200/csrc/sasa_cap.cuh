@@ -29,6 +29,9 @@
 #ifndef SASA_CAP_RING1
 #define SASA_CAP_RING1 1       // ring tests: one loop over the lane's whole 128-bit mask (0: one loop per 32-point word)
 #endif
+#ifndef SASA_CAP_LD256
+#define SASA_CAP_LD256 1       // one 256-bit load per bin (LDG.E.256, sm_100) instead of two 128-bit loads
+#endif
 #ifndef SASA_CAP_R2
 #define SASA_CAP_R2 1          // rounds 0 and 1 (the first 64 neighbours) are fetched together: one OR-reduction for both, the
                                // ring tests of round 0 already see the inner masks of round 1, and both fetches overlap
@@ -193,8 +196,14 @@ __device__ __forceinline__ CapRound cap_fetch(const uint4 *__restrict__ tab, con
     // (nearly) coincident centres: no direction -- the degenerate bin sends every point to the exact test
     const int bin = valid ? (vmag >= kCapMinV2 ? cap_bin(R.e, vmag) : (int)kCapBinDegenerate) : (int)kCapBinEmpty;
     const uint4 *b = tab + 2 * (size_t)(unsigned)bin;
+#if SASA_CAP_LD256
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(R.in.x), "=r"(R.in.y), "=r"(R.in.z), "=r"(R.in.w), "=r"(R.rg.x), "=r"(R.rg.y), "=r"(R.rg.z), "=r"(R.rg.w)
+        : "l"(b));
+#else
     R.in = __ldg(b);
     R.rg = __ldg(b + 1);
+#endif
     return R;
 }
 

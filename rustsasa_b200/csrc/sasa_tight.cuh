@@ -347,9 +347,9 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
 #else
     while (claim_structure(p, V.misc, sid, a0, N)) {
 #endif
-        Grid g;
+        Grid g0;   // also parked in V.misc by the setup (load_grid)
         int ncell;
-        const bool ok = structure_setup<NT, HAS_CLS, CMAX>(p, V, sid, a0, N, g, ncell);
+        const bool ok = structure_setup<NT, HAS_CLS, CMAX>(p, V, sid, a0, N, g0, ncell);
 #if SASA_OPT_NEXT
         if (warp == 0) claim_next_and_prefetch(p, V.misc);   // every structure, also after a rejected one
 #endif
@@ -433,7 +433,9 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
         }
 #else
             while (pos < pos_end) {
-                // the cell of atom `pos` and the end of its run in the sorted array
+                // the cell of atom `pos` and the end of its run in the sorted array (the grid is re-read from shared memory
+                // at every cell instead of pinning -- in practice spilling -- 8 registers through the loop)
+                const Grid g = load_grid(V.misc);
                 const float4 a_first = V.atom[pos];
                 const int cx = cell_coord(a_first.x, g.minx, g.inv_c, g.nx), cy = cell_coord(a_first.y, g.miny, g.inv_c, g.ny),
                           cz = cell_coord(a_first.z, g.minz, g.inv_c, g.nz);
