@@ -32,18 +32,25 @@ struct SmallLayout {
     size_t pts, ent, cand, list, red, misc, atom, val, cls, orig, cellw, total;
 };
 
+// Per-warp scratch is ONE contiguous block per warp -- entries | candidate lists | cell candidate list -- so that a single
+// warp base address serves all three with immediate offsets (three separate arrays cost three re-derived addresses
+// wherever the 64-register budget makes ptxas rematerialise them).
+constexpr size_t kWarpOffCand = (size_t)kNbCap * 16, kWarpOffList = kWarpOffCand + (size_t)kCandSlots * 2,
+                 kWarpBlockBytes = (kWarpOffList + (size_t)kListCap * 2 + 15) & ~(size_t)15;
+constexpr size_t kOffWarpBlocks = 128 * 16;
+
 __host__ __device__ constexpr size_t small_fixed_bytes(int nwarps) {
-    return 128 * 16 + (size_t)nwarps * kNbCap * 16 + (size_t)nwarps * kCandSlots * 2 + (size_t)nwarps * kListCap * 2 +
-           32 * 8 * 4 + 64;
+    return kOffWarpBlocks + (size_t)nwarps * kWarpBlockBytes + 32 * 8 * 4 + 64;
 }
 
 __host__ __device__ constexpr SmallLayout small_layout(uint32_t nmax, uint32_t cmax, int nwarps, bool has_cls) {
     SmallLayout L{};
     size_t o = 0;
     L.pts = o;   o += 128 * 16;
-    L.ent = o;   o += (size_t)nwarps * kNbCap * 16;
-    L.cand = o;  o += (size_t)nwarps * kCandSlots * 2;
-    L.list = o;  o += (size_t)nwarps * kListCap * 2;
+    L.ent = o;                                  // warp w: ent at L.ent + w * kWarpBlockBytes,
+    L.cand = o + kWarpOffCand;                  //         cand at + kWarpOffCand, list at + kWarpOffList
+    L.list = o + kWarpOffList;
+    o += (size_t)nwarps * kWarpBlockBytes;
     L.red = o;   o += 32 * 8 * 4;
     L.misc = o;  o += 64;
     L.atom = o;  o += ((size_t)nmax + 1) * 16;   // +1: the far-away sentinel atom the tight kernel pads its lists with
@@ -377,11 +384,11 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NW = NT / 32;
     constexpr uint32_t NMAX = max_atoms(NT, MINB, CMAX, HAS_CLS);
-    constexpr size_t kOffEnt = 128 * 16, kOffCand = kOffEnt + (size_t)NW * kNbCap * 16;
     const SmemView V = smem_view<NT, HAS_CLS, NMAX, CMAX>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 *const w_ent = reinterpret_cast<float4 *>(smem + kOffEnt) + warp * kNbCap;
-    uint16_t *const w_cand = reinterpret_cast<uint16_t *>(smem + kOffCand) + warp * kCandSlots;
+    unsigned char *const wblock = smem + kOffWarpBlocks + (size_t)warp * kWarpBlockBytes;
+    float4 *const w_ent = reinterpret_cast<float4 *>(wblock);
+    uint16_t *const w_cand = reinterpret_cast<uint16_t *>(wblock + kWarpOffCand);
     const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0;
     const float4 *s_pts = p.n_points <= 128 ? V.ptab : nullptr;
     stage_points(p, V.ptab);

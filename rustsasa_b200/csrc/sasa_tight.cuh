@@ -54,6 +54,13 @@ namespace sasa {
 #define SASA_OPT_ACLAIM 4     // > 0: warps claim runs of ATOMS (at least this many) of the cell-sorted order instead of runs
                               // of cells -- finer tail at the price of some cells' candidate lists being built twice
 #endif
+#ifndef SASA_OPT_SNAP
+#define SASA_OPT_SNAP 1       // atom-granular claims are snapped to whole cells: a cell is worked by the warp whose claim holds
+                              // the cell's first atom, so no candidate list is built twice
+#endif
+#ifndef SASA_OPT_GRIDLD
+#define SASA_OPT_GRIDLD 0     // the grid is re-read from shared memory at every cell instead of living in (spilled) registers
+#endif
 #ifndef SASA_OPT_PIPE
 #define SASA_OPT_PIPE 0       // cap path: an atom's first table round is fetched asynchronously (LDGSTS into the warp's staging
                               // area) and consumed after the NEXT atom's neighbour search
@@ -326,13 +333,12 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NW = NT / 32;
     constexpr uint32_t NMAX = max_atoms(NT, MINB, CMAX, HAS_CLS);
-    constexpr size_t kOffEnt = 128 * 16, kOffCand = kOffEnt + (size_t)NW * kNbCap * 16,
-                     kOffList = kOffCand + (size_t)NW * kCandSlots * 2;
     const SmemView V = smem_view<NT, HAS_CLS, NMAX, CMAX>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4 *const w_ent = reinterpret_cast<float4 *>(smem + kOffEnt) + warp * kNbCap;
-    uint16_t *const w_cand = reinterpret_cast<uint16_t *>(smem + kOffCand) + warp * kCandSlots;
-    uint16_t *const w_list = reinterpret_cast<uint16_t *>(smem + kOffList) + warp * kListCap;
+    unsigned char *const wblock = smem + kOffWarpBlocks + (size_t)warp * kWarpBlockBytes;
+    float4 *const w_ent = reinterpret_cast<float4 *>(wblock);
+    uint16_t *const w_cand = reinterpret_cast<uint16_t *>(wblock + kWarpOffCand);
+    uint16_t *const w_list = reinterpret_cast<uint16_t *>(wblock + kWarpOffList);
     stage_points(p, V.ptab);
     const int nbody = (int)min(p.n_points, p.n_body), nsl = (nbody + 31) >> 5;
     const int tail_sh = tile_shift(max(1, min(32, (int)p.n_points - nbody)));
@@ -432,14 +438,35 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
             }
         }
 #else
+#if SASA_OPT_ACLAIM > 0 && SASA_OPT_SNAP
+            {   // the cell that holds the first claimed atom started in an earlier claim: its owner finishes it
+#if SASA_OPT_GRIDLD
+                const Grid g = load_grid(V.misc);
+#else
+                const Grid g = g0;
+#endif
+                const float4 a = V.atom[pos];
+                const int c = (cell_coord(a.z, g.minz, g.inv_c, g.nz) * g.ny + cell_coord(a.y, g.miny, g.inv_c, g.ny)) * g.nx +
+                              cell_coord(a.x, g.minx, g.inv_c, g.nx);
+                if ((int)V.cell[c] < pos) pos = (int)V.cell[c + 1];
+            }
+#endif
             while (pos < pos_end) {
                 // the cell of atom `pos` and the end of its run in the sorted array (the grid is re-read from shared memory
                 // at every cell instead of pinning -- in practice spilling -- 8 registers through the loop)
+#if SASA_OPT_GRIDLD
                 const Grid g = load_grid(V.misc);
+#else
+                const Grid g = g0;
+#endif
                 const float4 a_first = V.atom[pos];
                 const int cx = cell_coord(a_first.x, g.minx, g.inv_c, g.nx), cy = cell_coord(a_first.y, g.miny, g.inv_c, g.ny),
                           cz = cell_coord(a_first.z, g.minz, g.inv_c, g.nz);
+#if SASA_OPT_ACLAIM > 0 && SASA_OPT_SNAP
+                const int cell_end = (int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1];   // whole cells, past pos_end if need be
+#else
                 const int cell_end = min((int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1], pos_end);
+#endif
                 const int total = tight_fill_list(g, V.cell, cx, cy, cz, w_list, N);
                 for (; pos < cell_end; ++pos) {
                     const float4 ai = V.atom[pos];
