@@ -186,11 +186,14 @@ struct CapRound {
 };
 
 // Lane `lane` of the round starting at q0: entry + table fetch (lanes past k fetch the empty bin).
-__device__ __forceinline__ CapRound cap_fetch(const uint4 *__restrict__ tab, const float4 *s_atom, const float4 ai, float probe,
-                                              float r2, float two_r, const uint16_t *cand, int q, int k) {
+// Atoms: accessor of the cell-sorted atoms (shared-memory array in the fused kernel, global array in the large-structure path);
+// IdxT: type of the candidate positions.
+template <class Atoms, class IdxT>
+__device__ __forceinline__ CapRound cap_fetch(const uint4 *__restrict__ tab, const Atoms &s_atom, const float4 ai, float probe,
+                                              float r2, float two_r, const IdxT *cand, int q, int k) {
     CapRound R;
     const bool valid = q < k;
-    const float4 aj = s_atom[valid ? (int)cand[q] : 0];
+    const float4 aj = s_atom(valid ? (int)cand[q] : 0);
     float vmag;
     R.e = make_entry(ai, aj, probe, r2, two_r, &vmag);
     // (nearly) coincident centres: no direction -- the degenerate bin sends every point to the exact test
@@ -225,8 +228,9 @@ __device__ __forceinline__ int cap_covered(unsigned a0, unsigned a1, unsigned a2
 // Lane q of round r owns neighbour 32 r + q: it builds the entry with the reference's arithmetic (make_entry), fetches
 // its bin's masks, and -- after the warp-wide OR of the inner masks -- runs the exact test on its own ring points that
 // are still uncovered.  Hits are folded into the next OR.
-__device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const float4 *s_atom, const float4 ai, float probe,
-                                        const uint16_t *cand, int k, const float4 *pts, int n_points, int nbody) {
+template <class Atoms, class IdxT>
+__device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const Atoms &s_atom, const float4 ai, float probe,
+                                        const IdxT *cand, int k, const float4 *pts, int n_points, int nbody) {
     const int lane = lane_id();
     const float r = __fadd_rn(ai.w, probe);
     const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
@@ -266,55 +270,6 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const flo
         cap_round(R, pts, nbody, a0, a1, a2, a3);
     }
 #endif
-    return n_points - cap_covered(a0, a1, a2, a3);
-}
-
-// ---- the same, split in two so that the table latency of an atom's first round hides behind the neighbour search of the
-// next atom: cap_issue builds the entries of round 0, parks them in the warp's staging area and starts the asynchronous
-// copy (LDGSTS, no registers in flight) of their bins' masks into it; cap_finish waits for the copy and does the rest.
-// Staging layout (kCapStageBytes per warp): float4 e[32] | uint4 inner[32] | uint4 ring[32].
-constexpr int kCapStageBytes = 96 * 16;
-
-__device__ __forceinline__ void cap_issue(const uint4 *__restrict__ tab, const float4 *s_atom, const float4 ai, float probe,
-                                          const uint16_t *cand, int k, float4 *stage) {
-    const int lane = lane_id();
-    const float r = __fadd_rn(ai.w, probe);
-    const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
-    const bool valid = lane < k;
-    const float4 aj = s_atom[valid ? (int)cand[lane] : 0];
-    float vmag;
-    const float4 e = make_entry(ai, aj, probe, r2, two_r, &vmag);
-    const int bin = valid ? (vmag >= kCapMinV2 ? cap_bin(e, vmag) : (int)kCapBinDegenerate) : (int)kCapBinEmpty;
-    stage[lane] = e;
-    const uint4 *b = tab + 2 * (size_t)(unsigned)bin;
-    const unsigned d_in = (unsigned)__cvta_generic_to_shared(stage + 32 + lane);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d_in), "l"(b));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d_in + 32 * 16), "l"(b + 1));
-    asm volatile("cp.async.commit_group;");
-}
-
-__device__ __forceinline__ int cap_finish(const uint4 *__restrict__ tab, const float4 *s_atom, const float4 ai, float probe,
-                                          const uint16_t *cand, int k, const float4 *pts, int n_points, int nbody,
-                                          const float4 *stage) {
-    const int lane = lane_id();
-    unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    {
-        CapRound R;     // every lane reads back what it staged itself
-        R.e = stage[lane];
-        R.in = reinterpret_cast<const uint4 *>(stage)[32 + lane];
-        R.rg = reinterpret_cast<const uint4 *>(stage)[64 + lane];
-        cap_round(R, pts, nbody, a0, a1, a2, a3);
-    }
-    if (k > 32) {
-        const float r = __fadd_rn(ai.w, probe);
-        const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
-#pragma unroll 1
-        for (int q0 = 32; q0 < k; q0 += 32) {
-            const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, q0 + lane, k);
-            cap_round(R, pts, nbody, a0, a1, a2, a3);
-        }
-    }
     return n_points - cap_covered(a0, a1, a2, a3);
 }
 

@@ -6,6 +6,7 @@
 // Replaces SpatialGrid::new / build_all_neighbor_lists (src/structures/spatial_grid.rs:28-465), which the
 // reference runs serially, for N up to 2^32 / 16 atoms.
 #pragma once
+#include "sasa_cap.cuh"
 #include "sasa_device.cuh"
 
 namespace sasa {
@@ -258,6 +259,8 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
     const bool force_stream = (p.flags & 2u) != 0, stats = (p.flags & 1u) != 0, use_cache = (p.flags & 4u) == 0;
     unsigned long long pairs = 0, streamed = 0;
     const float4 *s_pts = p.n_points <= 128 ? s_ptab : nullptr;
+    const bool use_cap = p.cap != nullptr && p.n_points <= 128;
+    const int nbody = (int)min(p.n_points, p.n_body);
     if (threadIdx.x < 128) {
         const bool v = threadIdx.x < p.n_points;
         s_ptab[threadIdx.x] = make_float4(v ? __ldg(p.px + threadIdx.x) : 0.f, v ? __ldg(p.py + threadIdx.x) : 0.f,
@@ -286,7 +289,11 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
                 k = cc.total >= 0 ? gather_cached(p, atoms, cls_sorted, pos, ai, cc, w_cand)
                                   : gather_candidates(p, g, atoms, cells, cls_sorted, pos, ai, w_cand);
             }
-            if (k >= 0) {
+            if (k >= 0 && use_cap) {
+                // n_points <= 128: the cap-table occlusion of the fused kernel (sasa_cap.cuh), atoms read from global memory
+                cnt = (float)cap_atom(p.cap, atoms, ai, p.probe, w_cand, k, s_ptab, (int)p.n_points, nbody);
+                pairs += (unsigned)k;
+            } else if (k >= 0) {
                 const float r = __fadd_rn(ai.w, p.probe);
                 const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
                 cnt = atom_fast(p, w_ent, k, nfront, reinterpret_cast<uint16_t *>(w_cand), s_pts);

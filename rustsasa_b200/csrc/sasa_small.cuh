@@ -382,7 +382,6 @@ __device__ __forceinline__ bool claim_prefetched(int *misc, uint32_t &sid, uint3
 template <int NT, int MINB, bool HAS_CLS, uint32_t CMAX>
 __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int NW = NT / 32;
     constexpr uint32_t NMAX = max_atoms(NT, MINB, CMAX, HAS_CLS);
     const SmemView V = smem_view<NT, HAS_CLS, NMAX, CMAX>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

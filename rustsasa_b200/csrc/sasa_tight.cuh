@@ -61,10 +61,6 @@ namespace sasa {
 #ifndef SASA_OPT_GRIDLD
 #define SASA_OPT_GRIDLD 0     // the grid is re-read from shared memory at every cell instead of living in (spilled) registers
 #endif
-#ifndef SASA_OPT_PIPE
-#define SASA_OPT_PIPE 0       // cap path: an atom's first table round is fetched asynchronously (LDGSTS into the warp's staging
-                              // area) and consumed after the NEXT atom's neighbour search
-#endif
 #ifndef SASA_OPT_NEXT
 #define SASA_OPT_NEXT 1       // warp 0 claims the CTA's next structure and prefetches its atoms into L2 while the other
                               // warps already work on the current one (hides the claim / first-touch latency of the setup)
@@ -341,6 +337,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
     uint16_t *const w_list = reinterpret_cast<uint16_t *>(wblock + kWarpOffList);
     stage_points(p, V.ptab);
     const int nbody = (int)min(p.n_points, p.n_body), nsl = (nbody + 31) >> 5;
+    (void)nsl;
     const int tail_sh = tile_shift(max(1, min(32, (int)p.n_points - nbody)));
     const float reach0 = 2.0f * p.probe + kCutSlack;
 
@@ -391,53 +388,6 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
             int pos = (int)V.cell[c0];
             const int pos_end = (int)V.cell[c1];
 #endif
-#if SASA_OPT_CAP && SASA_OPT_PIPE
-            // software pipeline over the atoms of the run, one flat loop (a single inlined copy of every stage):
-            //   gather(i) | finish(i - 1) | issue(i)      -- the table masks of atom i are in flight during gather(i + 1)
-            // st = the atom in flight: pos | k << 16 | candidate buffer << 24, or -1
-            int st = -1, cell_end = pos, total = 0;
-            for (;;) {
-                const bool have = pos < pos_end;
-                const int cb = st >= 0 ? ((st >> 24) ^ 1) : 0;
-                int k = 0;
-                if (have) {
-                    const float4 ai = V.atom[pos];
-                    if (pos >= cell_end) {   // first atom of a cell: its candidate list (the grid is re-read from shared
-                        const Grid g = load_grid(V.misc);   // memory here instead of pinning 8 registers through the loop)
-                        const int cx = cell_coord(ai.x, g.minx, g.inv_c, g.nx), cy = cell_coord(ai.y, g.miny, g.inv_c, g.ny),
-                                  cz = cell_coord(ai.z, g.minz, g.inv_c, g.nz);
-                        cell_end = min((int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1], pos_end);
-                        total = tight_fill_list(g, V.cell, cx, cy, cz, w_list, N);
-                    }
-                    k = total >= 0 ? tight_gather<HAS_CLS>(V.atom, V.cls, w_list, total, pos, ai, ai.w + reach0, w_cand + cb * kQueueCap)
-                                   : kNbCap + 1;
-                }
-                if (st >= 0) {
-                    const int ppos = st & 0xffff;
-                    const int cnt = cap_finish(p.cap, V.atom, V.atom[ppos], p.probe, w_cand + (cb ^ 1) * kQueueCap, (st >> 16) & 0xff,
-                                               V.ptab, (int)p.n_points, nbody, w_ent);
-                    if (lane == 0) {
-                        V.val[V.orig[ppos]] = (float)cnt;
-                        atomicAdd(&V.misc[6], (st >> 16) & 0xff);
-                    }
-                    st = -1;
-                    __syncwarp();
-                }
-                if (!have) break;
-                if (k <= kNbCap) {
-                    cap_issue(p.cap, V.atom, V.atom[pos], p.probe, w_cand + cb * kQueueCap, k, w_ent);
-                    st = pos | (k << 16) | (cb << 24);
-                } else {
-                    const int cnt = tight_cold_atom<HAS_CLS>(p.px, p.py, p.pz, p.n_points, p.n_body, p.probe, p.near2, p.m_min,
-                                                             p.m_max, load_grid(V.misc), V.atom, V.cell, V.cls, V.ptab, pos, w_ent,
-                                                             w_cand + cb * kQueueCap, V.misc);
-                    if (lane == 0) V.val[V.orig[pos]] = (float)cnt;
-                    __syncwarp();
-                }
-                ++pos;
-            }
-        }
-#else
 #if SASA_OPT_ACLAIM > 0 && SASA_OPT_SNAP
             {   // the cell that holds the first claimed atom started in an earlier claim: its owner finishes it
 #if SASA_OPT_GRIDLD
@@ -475,7 +425,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                                        : kNbCap + 1;
                     if (k <= kNbCap) {
 #if SASA_OPT_CAP
-                        cnt = cap_atom(p.cap, V.atom, ai, p.probe, w_cand, k, V.ptab, (int)p.n_points, nbody);
+                        cnt = cap_atom(p.cap, SmemAtoms{V.atom}, ai, p.probe, w_cand, k, V.ptab, (int)p.n_points, nbody);
 #else
                         const float r = __fadd_rn(ai.w, p.probe);
                         const int nfront = tight_entries(V.atom, ai, p.probe, __fmul_rn(r, r), __fmul_rn(2.0f, r), p.near2,
@@ -504,7 +454,6 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                 }
             }
         }
-#endif
         if (lane == 0 && pairs) atomicAdd(&V.misc[6], (int)pairs);
         __syncthreads();
         if (threadIdx.x == 0 && p.stat) {
