@@ -10,7 +10,7 @@
 //   rust_sasa::SASACalcError                                                          src/options.rs:466-494
 //   rust_sasa::{get_radius, get_protor_radius, load_radii_from_file, serialize_chain_id}
 //                                                                                     src/utils.rs:24-56, src/utils/consts.rs:31-91
-//   rust_sasa::{sasa_result_to_json, sasa_result_to_xml}                              src/utils/io.rs:11-18
+//   rust_sasa::{sasa_result_to_json, sasa_result_to_xml, sasa_result_to_protein_object} src/utils/io.rs:11-64
 //   rust_sasa::pdb::{PDB, open}   the part of pdbtbx's hierarchy the path reads       pdbtbx/src/read/**, structs/**
 // plus `process_many`, the batched form that the CLI's directory mode (src/main.rs:342-480) maps onto: all
 // structures of a tile go through ONE pipelined sasa_b200_batch_run_host call.
@@ -102,6 +102,9 @@ struct AtomRec {
     double x, y, z;
     double occupancy;
     std::string element;   // upper-case symbol, empty = unknown
+    double b_factor = 0.0; // what sasa_result_to_protein_object overwrites
+    int charge = 0;
+    std::string id;        // pdbtbx Atom::id: _atom_site.id (mmCIF) or the 0-based running atom count of the file (PDB)
 };
 
 struct Conformer {
@@ -139,6 +142,15 @@ struct PDB {
 PDB read_pdb(const std::string &path);      // throws std::runtime_error on I/O failure
 PDB read_mmcif(const std::string &path);
 PDB open(const std::string &path);          // by extension: .cif / .mmcif -> mmCIF, else PDB
+
+// Coordinate-section writers after pdbtbx::save (pdbtbx/src/save/pdb.rs:507-613, save/mmcif.rs:225-412, StrictnessLevel::Loose):
+// MODEL / ATOM / HETATM / TER / ENDMDL / END with pdbtbx's field rules, and the _atom_site loop with its columns.  Header
+// records (HEADER, REMARK, CRYST1, SCALE, ...) are not kept by the reader above and are not written.
+void save_pdb(const PDB &pdb, const std::string &path);     // throws std::runtime_error when the file cannot be written
+void save_mmcif(const PDB &pdb, const std::string &path);
+void save(const PDB &pdb, const std::string &path);         // by extension: .pdb / .cif / .mmcif, anything else is an error
+std::string to_pdb_string(const PDB &pdb);
+std::string to_mmcif_string(const PDB &pdb, const std::string &name = "sasa_b200");
 
 }  // namespace pdb
 
@@ -233,6 +245,12 @@ private:
 // ---- src/utils/io.rs:11-18 ---------------------------------------------------------------------------------------
 std::string sasa_result_to_json(const SASAResult &result);   // serde_json::to_string of the externally tagged enum
 std::string sasa_result_to_xml(const SASAResult &result);    // quick_xml::se::to_string
+// src/utils/io.rs:20-64: writes the result into the B-factors of `original_pdb`, with the reference's own iteration rules
+// (Atom: the i-th atom of pdb.atoms() over ALL atoms -- every conformer, hydrogens and HETATMs included -- gets v[i];
+// Residue / Chain: the i-th residue / chain over all models, the serial number / chain id is checked; Protein: every atom
+// gets global_total).  Throws std::runtime_error where the reference returns Err or panics (index past the result
+// vector, mismatched residue, negative or non-finite value).
+void sasa_result_to_protein_object(pdb::PDB &original_pdb, const SASAResult &result);
 
 // Engine selection for this process: CUDA device ordinal used by every call above (default: SASA_B200_DEVICE or 0).
 void set_device(int device);

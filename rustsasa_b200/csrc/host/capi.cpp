@@ -86,6 +86,52 @@ HOST_API long sasa_b200_host_format(int xml, int kind, const float *values, size
     std::memcpy(out, s.c_str(), s.size() + 1);
     return (long)s.size();
 }
+// B-factor write-back on hand-made values (CPU-only tests of src/utils/io.rs:20-64 and of the coordinate writers):
+// kind 0 atom (values[i] per atom), 1 residue (values[i] per residue of the file, in order), 2 chain, 3 protein
+// (values[0..3]); `bad_serial` != 0 corrupts the first residue's serial number to exercise the reference's assert.
+// Output text: format 0 = PDB, 1 = mmCIF.  Returns the text length, or -1 with err filled.
+HOST_API long sasa_b200_host_writeback(const char *path, int kind, const float *values, size_t n, int bad_serial, int format,
+                                       char *out, size_t outlen, char *err, size_t errlen) {
+    try {
+        pdb::PDB st = pdb::open(path);
+        SASAResult r;
+        if (kind == 0) {
+            r = std::vector<float>(values, values + n);
+        } else if (kind == 1) {
+            std::vector<ResidueResult> v;
+            for (const auto &m : st.models)
+                for (const auto &ch : m.chains)
+                    for (const auto &res : ch.residues) {
+                        if (v.size() >= n) break;
+                        const std::string name = res.name().value_or("");
+                        v.push_back(ResidueResult{res.serial + (bad_serial && v.empty() ? 1 : 0), res.icode, values[v.size()], name,
+                                                  is_polar_residue(name), ch.id});
+                    }
+            r = std::move(v);
+        } else if (kind == 2) {
+            std::vector<ChainResult> v;
+            for (const auto &m : st.models)
+                for (const auto &ch : m.chains) {
+                    if (v.size() >= n) break;
+                    v.push_back(ChainResult{ch.id, values[v.size()]});
+                }
+            r = std::move(v);
+        } else {
+            r = ProteinResult{values[0], values[1], values[2]};
+        }
+        sasa_result_to_protein_object(st, r);
+        const std::string text = format == 1 ? pdb::to_mmcif_string(st, "?") : pdb::to_pdb_string(st);
+        if (text.size() + 1 > outlen) {
+            put_error(err, errlen, "IO: output buffer too small");
+            return -1;
+        }
+        std::memcpy(out, text.c_str(), text.size() + 1);
+        return (long)text.size();
+    } catch (const std::exception &e) {
+        put_error(err, errlen, std::string("ProteinSerialization: ") + e.what());
+    }
+    return -1;
+}
 HOST_API long sasa_b200_host_serialize_chain_id(const char *s) { return (long)serialize_chain_id(s); }
 HOST_API float sasa_b200_host_get_radius(const char *res, const char *atom) {
     auto r = get_radius(res, atom, nullptr);

@@ -7,7 +7,7 @@
 // in parallel (what src/main.rs:342-480 does with a rayon par_iter over files and a single-threaded engine call
 // each); per-file failures are collected, reported at the end and do not change the exit code (:447-479); outputs
 // are named {stem}.{ext} (:414-416).  A single-file failure exits non-zero.  `-t` is accepted and ignored.
-// Output formats: json and xml (pdb / cif B-factor write-back is not provided by this build).
+// Output formats: json, xml, and pdb / cif (B-factor write-back, src/utils/io.rs:20-64 + the coordinate writers of writers.cpp).
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -41,7 +41,7 @@ struct Args {
     std::fprintf(stderr,
                  "Usage: sasa_b200_cli [OPTIONS] <INPUT> <OUTPUT>\n"
                  "  -o, --output-depth <atom|residue|chain|protein>   [default: residue]\n"
-                 "  -f, --format <json|xml>        required for directories, else inferred from the extension\n"
+                 "  -f, --format <json|xml|pdb|cif> required for directories, else inferred from the extension (default json)\n"
                  "  -n, --n-points <N>             [default: 100]\n"
                  "  -p, --probe-radius <R>         [default: 1.4]\n"
                  "  -H, --include-hydrogens\n  -r, --radii-file <FILE>\n  -a, --allow-vdw-fallback\n  -e, --include-hetatms\n"
@@ -87,7 +87,17 @@ LevelKind level_of(const std::string &d) {
     usage("output depth must be atom, residue, chain or protein");
 }
 
-std::string render(const SASAResult &r, const std::string &format) { return format == "xml" ? sasa_result_to_xml(r) : sasa_result_to_json(r); }
+bool known_format(const std::string &f) { return f == "json" || f == "xml" || f == "pdb" || f == "cif"; }
+bool structure_format(const std::string &f) { return f == "pdb" || f == "cif"; }
+
+// src/main.rs:203-226: xml / json text, or the input structure with the result written into its B-factors
+std::string render(const SASAResult &r, const std::string &format, const pdb::PDB *original) {
+    if (format == "xml") return sasa_result_to_xml(r);
+    if (!structure_format(format)) return sasa_result_to_json(r);
+    pdb::PDB copy = *original;
+    sasa_result_to_protein_object(copy, r);
+    return format == "pdb" ? pdb::to_pdb_string(copy) : pdb::to_mmcif_string(copy, "?");
+}
 
 bool write_file(const fs::path &p, const std::string &text, std::string *err) {
     std::ofstream fh(p, std::ios::binary);
@@ -138,8 +148,8 @@ int main(int argc, char **argv) {
             std::fprintf(stderr, "error: --format is required when processing a directory\n");
             return 1;
         }
-        if (format != "json" && format != "xml") {
-            std::fprintf(stderr, "error: output format '%s' is not provided by this build (json, xml)\n", format.c_str());
+        if (!known_format(format)) {
+            std::fprintf(stderr, "error: invalid value '%s' for '--format' (json, xml, pdb, cif)\n", format.c_str());
             return 1;
         }
         fs::create_directories(args.output, ec);
@@ -160,10 +170,13 @@ int main(int argc, char **argv) {
             const size_t f1 = std::min(files.size(), f0 + args.tile), n = f1 - f0;
             // 1. parse + extract in parallel
             std::vector<std::optional<Packed>> packed(n);
+            std::vector<std::optional<pdb::PDB>> kept(structure_format(format) ? n : 0);   // only the write-back formats need them
             parallel_for(n, [&](size_t i) {
                 const fs::path &p = files[f0 + i];
                 try {
-                    packed[i] = build_atoms_and_mapping(pdb::open(p.string()), level, opt);
+                    pdb::PDB st = pdb::open(p.string());
+                    packed[i] = build_atoms_and_mapping(st, level, opt);
+                    if (!kept.empty()) kept[i] = std::move(st);
                 } catch (const std::exception &e) {
                     add_error("Error processing " + p.stem().string() + ": " + e.what());
                 }
@@ -194,8 +207,14 @@ int main(int argc, char **argv) {
                     return;
                 }
                 std::string werr;
-                if (!write_file(fs::path(args.output) / (p.stem().string() + "." + format), render(std::get<SASAResult>(out[k]), format), &werr))
-                    add_error("Error processing " + p.stem().string() + ": " + werr);
+                try {
+                    const pdb::PDB *orig = kept.empty() ? nullptr : &*kept[good_idx[k]];
+                    if (!write_file(fs::path(args.output) / (p.stem().string() + "." + format),
+                                    render(std::get<SASAResult>(out[k]), format, orig), &werr))
+                        add_error("Error processing " + p.stem().string() + ": " + werr);
+                } catch (const std::exception &e) {   // CLIError::ProteinSerialization
+                    add_error("Error processing " + p.stem().string() + ": " + e.what());
+                }
             });
         }
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -214,10 +233,10 @@ int main(int argc, char **argv) {
     if (format.empty()) {
         std::string ext = fs::path(args.output).extension().string();
         if (!ext.empty()) ext.erase(0, 1);
-        format = ext;
+        format = known_format(ext) ? ext : "json";   // OutputFormat::from_file_extension: anything else is JSON (src/main.rs:45-53)
     }
-    if (format != "json" && format != "xml") {
-        std::fprintf(stderr, "error: output format '%s' is not provided by this build (json, xml)\n", format.c_str());
+    if (!known_format(format)) {
+        std::fprintf(stderr, "error: invalid value '%s' for '--format' (json, xml, pdb, cif)\n", format.c_str());
         return 1;
     }
     if (fs::is_directory(args.output, ec)) {
@@ -229,7 +248,7 @@ int main(int argc, char **argv) {
         auto out = process_many({&st}, level, opt);
         if (auto *err = std::get_if<SASACalcError>(&out[0])) throw *err;
         std::string werr;
-        if (!write_file(args.output, render(std::get<SASAResult>(out[0]), format), &werr)) throw std::runtime_error(werr);
+        if (!write_file(args.output, render(std::get<SASAResult>(out[0]), format, &st), &werr)) throw std::runtime_error(werr);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

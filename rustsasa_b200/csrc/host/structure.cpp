@@ -265,6 +265,7 @@ PDB read_pdb(const std::string &path) {
     PDB pdb;
     Model model;
     long serial_add = 0, res_add = 0, last_serial = -1, last_res = -1;
+    unsigned long long atom_id = 0;   // pdbtbx's id iterator (pdbtbx/src/read/pdb/parser.rs:116)
     std::string line;
     while (std::getline(fh, line)) {
         if (!line.empty() && line.back() == '\r') line.pop_back();
@@ -291,7 +292,15 @@ PDB read_pdb(const std::string &path) {
             a.y = parse_double(std::string_view(line).substr(38, 8));
             a.z = parse_double(std::string_view(line).substr(46, 8));
             a.occupancy = occ_s.empty() ? 1.0 : parse_double(occ_s);
+            {
+                const std::string_view b_s = trim(std::string_view(line).substr(60, 6));
+                a.b_factor = b_s.empty() ? 0.0 : parse_double(b_s);
+                // columns 79-80: charge as digit + sign ("1+", "2-")
+                const char cd = line[78], cs = line[79];
+                if (cd >= '0' && cd <= '9' && (cs == '+' || cs == '-')) a.charge = (cs == '-' ? -1 : 1) * (cd - '0');
+            }
             a.element = resolve_element(std::string_view(line).substr(76, 2), name);
+            a.id = std::to_string(atom_id++);
             add_atom(model, chain_c == ' ' ? std::string("A") : std::string(1, chain_c), resseq + res_add,
                      icode == ' ' ? std::string() : std::string(1, icode), resname, alt == ' ' ? std::string() : std::string(1, alt),
                      std::move(a));
@@ -402,6 +411,9 @@ PDB read_mmcif(const std::string &path) {
                 a.y = (v = get(tok, "Cartn_y")) ? parse_double(*v) : 0.0;
                 a.z = (v = get(tok, "Cartn_z")) ? parse_double(*v) : 0.0;
                 a.occupancy = (v = get(tok, "occupancy")) ? parse_double(*v) : 1.0;
+                a.b_factor = (v = get(tok, "B_iso_or_equiv")) ? parse_double(*v) : 0.0;
+                a.id = (v = get(tok, "id")) ? *v : std::to_string(model.atom_count);
+                if ((v = get(tok, "pdbx_formal_charge")) && !v->empty() && *v != "?" && *v != ".") a.charge = (int)parse_long(*v);
                 a.element = resolve_element((v = get(tok, "type_symbol")) ? *v : "", name);
                 const std::string *icode = get(tok, "pdbx_PDB_ins_code"), *alt = get(tok, "label_alt_id");
                 add_atom(model, chain ? *chain : std::string(), seq ? parse_long(*seq) : 0, icode ? *icode : std::string(), resname,

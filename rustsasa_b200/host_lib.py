@@ -45,6 +45,8 @@ def load() -> C.CDLL:
         L.sasa_b200_host_process_json.restype = C.c_long
         L.sasa_b200_host_format.argtypes = [C.c_int, C.c_int, vp, sz, C.c_char_p, sz]
         L.sasa_b200_host_format.restype = C.c_long
+        L.sasa_b200_host_writeback.argtypes = [C.c_char_p, C.c_int, vp, sz, C.c_int, C.c_int, C.c_char_p, sz, C.c_char_p, sz]
+        L.sasa_b200_host_writeback.restype = C.c_long
         L.sasa_b200_host_serialize_chain_id.argtypes = [C.c_char_p]
         L.sasa_b200_host_serialize_chain_id.restype = C.c_long
         L.sasa_b200_host_get_radius.argtypes = [C.c_char_p, C.c_char_p]
@@ -94,3 +96,16 @@ def format_values(values, xml=False, kind="atom") -> str:
     out = C.create_string_buffer(1 << 20)
     n = load().sasa_b200_host_format(int(xml), LEVELS[kind], v.ctypes.data, v.size, out, len(out))
     return out.raw[:n].decode()
+
+
+def writeback(path: str, kind: str, values, fmt: str = "pdb", bad_serial: bool = False) -> str:
+    """sasa_result_to_protein_object with hand-made values on a file, then the pdbtbx-style text (fmt: "pdb" | "cif")."""
+    L = load()
+    v = np.ascontiguousarray(values, dtype=np.float32)
+    out = C.create_string_buffer(1 << 24)
+    err = C.create_string_buffer(512)
+    n = L.sasa_b200_host_writeback(path.encode(), LEVELS[kind], v.ctypes.data, v.size, int(bad_serial), 1 if fmt == "cif" else 0,
+                                   out, len(out), err, 512)
+    if n < 0:
+        raise HostError(err.value.decode())
+    return out.value.decode()

@@ -101,3 +101,33 @@ def test_cli_single_file_mode(host, eng, tmp_path):
     assert_json_equals(out.read_text(), py_result(eng, os.path.join(DATA, "mini.cif"), "atom", n_points=200, probe_radius=1.2), "atom")
     r = subprocess.run([host.CLI_PATH, os.path.join(DATA, "mini.cif"), str(tmp_path)], capture_output=True, text=True)
     assert r.returncode != 0                                     # output path is a directory / no format
+
+
+def test_cli_structure_output_formats(host, eng, tmp_path):
+    """pdb / cif output = the input structure with the result in its B-factors (src/main.rs:212-225, src/utils/io.rs:20-64):
+    residue level in single-file mode, chain level in directory mode; every atom of a residue / chain carries that
+    residue's / chain's value as printed by pdbtbx's writers ({:6.2} in PDB, print_float in mmCIF)."""
+    src = os.path.join(DATA, "mini.cif")
+    want = json.loads(host.process_json(src, "residue"))["Residue"]
+    out = tmp_path / "o.pdb"
+    r = subprocess.run([host.CLI_PATH, src, str(out), "-o", "residue"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in out.read_text().splitlines() if l.startswith(("ATOM", "HETATM"))]
+    by_res = {}
+    for l in lines:
+        by_res.setdefault((l[21], int(l[22:26])), set()).add(l[60:66])
+    assert len(by_res) == len(want)
+    for item in want:
+        assert by_res[(item["chain_id"], item["serial_number"])] == {("%6.2f" % item["value"])[-6:]}
+    # directory mode, mmCIF, chain level
+    ind, outd = tmp_path / "in", tmp_path / "out"
+    ind.mkdir()
+    shutil.copy(src, ind / "mini.cif")
+    r = subprocess.run([host.CLI_PATH, str(ind), str(outd), "-f", "cif", "-o", "chain"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    chains = {c["name"]: c["value"] for c in json.loads(host.process_json(src, "chain"))["Chain"]}
+    rows = [l.split() for l in (outd / "mini.cif").read_text().splitlines() if l.startswith(("ATOM", "HETATM"))]
+    assert rows and all(abs(float(r_[16]) - chains[r_[7]]) <= 5e-6 * max(1.0, chains[r_[7]]) + 1e-5 for r_ in rows)
+    # an unknown extension means JSON (OutputFormat::from_file_extension, src/main.rs:45-53)
+    r = subprocess.run([host.CLI_PATH, src, str(tmp_path / "o.txt"), "-o", "protein"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Protein" in json.loads((tmp_path / "o.txt").read_text())

@@ -162,3 +162,113 @@ def test_cli_argument_errors(host, tmp_path):
     assert r.returncode != 0 and "radii" in r.stderr.lower()
     r = subprocess.run([cli, "only_one_arg"], capture_output=True, text=True)
     assert r.returncode == 2
+
+
+# ---- B-factor write-back (src/utils/io.rs:20-64) and the coordinate writers after pdbtbx::save -----------------------
+# The four inputs below are the ones of the reference's own unit tests (src/utils/io.rs:73-247).
+IO_ATOM = """ATOM      1  N   ALA A   1      20.154  16.967  25.000  1.00 10.00           N
+ATOM      2  CA  ALA A   1      19.030  16.155  25.000  1.00 15.00           C
+ATOM      3  C   ALA A   1      17.948  16.712  25.000  1.00 20.00           C
+END
+"""
+IO_RESIDUE = """ATOM      1  N   ALA A   1      20.154  16.967  25.000  1.00 10.00           N
+ATOM      2  CA  ALA A   1      19.030  16.155  25.000  1.00 15.00           C
+ATOM      3  N   GLY A   2      17.948  16.712  25.000  1.00 20.00           N
+ATOM      4  CA  GLY A   2      16.500  17.000  25.000  1.00 25.00           C
+END
+"""
+IO_CHAIN = """ATOM      1  N   ALA A   1      20.154  16.967  25.000  1.00 10.00           N
+ATOM      2  CA  ALA A   1      19.030  16.155  25.000  1.00 15.00           C
+ATOM      3  N   GLY B   1      17.948  16.712  25.000  1.00 20.00           N
+ATOM      4  CA  GLY B   1      16.500  17.000  25.000  1.00 25.00           C
+END
+"""
+
+
+def b_factors_of_pdb_text(text):
+    return [float(l[60:66]) for l in text.splitlines() if l.startswith(("ATOM", "HETATM"))]
+
+
+def test_sasa_result_to_protein_object_reference_cases(host, tmp_path):
+    """test_sasa_result_to_protein_object_{atom,residue,chain,protein} of src/utils/io.rs:73-247."""
+    f = tmp_path / "a.pdb"
+    f.write_text(IO_ATOM)
+    assert b_factors_of_pdb_text(host.writeback(str(f), "atom", [5.0, 10.0, 15.0])) == [5.0, 10.0, 15.0]
+    f.write_text(IO_RESIDUE)
+    assert b_factors_of_pdb_text(host.writeback(str(f), "residue", [100.0, 200.0])) == [100.0, 100.0, 200.0, 200.0]
+    f.write_text(IO_CHAIN)
+    assert b_factors_of_pdb_text(host.writeback(str(f), "chain", [300.0, 400.0])) == [300.0, 300.0, 400.0, 400.0]
+    f.write_text(IO_ATOM)
+    assert b_factors_of_pdb_text(host.writeback(str(f), "protein", [500.0, 200.0, 300.0])) == [500.0, 500.0, 500.0]
+
+
+def test_writeback_failure_modes(host, tmp_path):
+    """Where the reference returns Err or panics: result shorter than pdb.atoms() (what an atom-level result with filtered
+    hydrogens / HETATMs runs into, src/utils/io.rs:26-29), residue serial mismatch (:37), negative / non-finite values
+    (pdbtbx set_b_factor)."""
+    f = tmp_path / "a.pdb"
+    f.write_text(IO_ATOM)
+    with pytest.raises(host.HostError, match="index out of bounds"):
+        host.writeback(str(f), "atom", [5.0, 10.0])
+    with pytest.raises(host.HostError, match="negative"):
+        host.writeback(str(f), "atom", [5.0, -1.0, 2.0])
+    with pytest.raises(host.HostError, match="not finite"):
+        host.writeback(str(f), "protein", [float("nan"), 0.0, 0.0])
+    f.write_text(IO_RESIDUE)
+    with pytest.raises(host.HostError, match="serial_number"):
+        host.writeback(str(f), "residue", [1.0, 2.0], bad_serial=True)
+
+
+def test_pdb_writer_follows_pdbtbx_field_rules(host, tmp_path):
+    """pdbtbx/src/save/pdb.rs:112-127, :520-581: every sized field is the last `width` characters of its text, leading
+    zeros trimmed, LEFT-aligned (so serial and residue numbers are left-aligned), TER after every chain, END last; values
+    wider than their field lose their leading characters (1234.5 in a {:6.2} field prints as 234.50)."""
+    f = tmp_path / "a.pdb"
+    f.write_text(IO_CHAIN.replace("  1.00 25.00           C", "  0.50 25.00           C1+"))
+    text = host.writeback(str(f), "chain", [300.0, 1234.5])
+    assert text.splitlines() == [
+        "ATOM  1     N    ALA A1         20.154  16.967  25.000  1.00300.00          N ",
+        "ATOM  2     CA   ALA A1         19.030  16.155  25.000  1.00300.00          C ",
+        "TER2          ALA A1   ",
+        "ATOM  3     N    GLY B1         17.948  16.712  25.000  1.00234.50          N ",
+        "ATOM  4     CA   GLY B1         16.500  17.000  25.000  0.50234.50          C 1+",
+        "TER4          GLY B1   ",
+        "END",
+    ]
+
+
+def test_mmcif_writer_and_round_trip(host, tmp_path):
+    """_atom_site loop of pdbtbx/src/save/mmcif.rs:262-412 (column set, base-26 label chain, 1-based label_seq_id, aligned
+    columns, print_float) and: what the writers emit, the reader takes back with the same atoms and B-factors."""
+    f = tmp_path / "a.pdb"
+    f.write_text(IO_CHAIN)
+    cif = host.writeback(str(f), "atom", [1.0, 2.5, 0.125, 1.4235263], fmt="cif")
+    rows = [l.split() for l in cif.splitlines() if l.startswith("ATOM")]
+    assert cif.startswith("data_?\n#\n_entry.id   ?\n#\n_audit_conform.dict_name       mmcif_pdbx.dic\n")
+    assert cif.rstrip().endswith("#") and cif.count("_atom_site.") == 19
+    assert rows[0] == ["ATOM", "0", "N", "N", ".", "ALA", "B", "A", "1", "1", "1", ".", "20.154", "16.967", "25.0", "1.0", "1.0",
+                       "0", "0"]   # model number 0: pdbtbx's default for PDB files without MODEL records (read/pdb/parser.rs:98)
+    assert rows[3][1] == "3" and rows[3][6:11] == ["C", "B", "2", "1", "1"] and rows[3][16] == "1.42353"
+    assert len({len(l) for l in cif.splitlines() if l.startswith("ATOM")}) == 1      # aligned table
+    # round trip through both formats
+    g = tmp_path / "b.cif"
+    g.write_text(cif)
+    back = host.writeback(str(g), "protein", [7.0, 0.0, 0.0], fmt="pdb")
+    assert b_factors_of_pdb_text(back) == [7.0] * 4
+    a = host.pack(str(f), "chain", allow_vdw_fallback=True)
+    b = host.pack(str(g), "chain", allow_vdw_fallback=True)
+    assert np.array_equal(a["xyzr"], b["xyzr"]) and np.array_equal(a["seg_be"], b["seg_be"])
+
+
+def test_writeback_on_altloc_and_multimodel_files(host):
+    """Atom-level write-back indexes ALL atoms of the hierarchy (every conformer of every model): the result vector must
+    be that long, which is the reference's behaviour (src/utils/io.rs:26-29) and the reason its CLI's atom-level pdb/cif
+    output only works on files without hydrogens, HETATMs and alternative locations."""
+    for name in ["mini_altloc.pdb", "mini_models.pdb"]:
+        path = os.path.join(DATA, name)
+        n_all = sum(1 for _ in b_factors_of_pdb_text(host.writeback(path, "protein", [1.0, 0.0, 0.0])))
+        vals = np.arange(n_all, dtype=np.float32)
+        assert b_factors_of_pdb_text(host.writeback(path, "atom", vals)) == vals.tolist()
+        if n_all > 1:
+            with pytest.raises(host.HostError):
+                host.writeback(path, "atom", vals[:-1])
