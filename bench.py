@@ -316,11 +316,12 @@ def main():
                           "e2e_device_span_ms": stats_e2e["kernel_ms"]},
         }
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:   # the CPU leg is an N = 1 measurement (rank 0 alone would stall the other ranks)
             cpu, cpu_out, (n, a1, g1) = cpu_sample(data)
             out["cpu_baseline"] = cpu
             out["parity_on_cpu_sample"] = bool(np.array_equal(cpu_out["seg"], np.asarray(h_res.seg_sasa)[:g1]))
-        k_mean = cpu["k_mean"] if cpu else 43.1
+        # without the CPU leg: the oracle's figure for this same seeded batch from the committed N = 1 run (profiles/r01h_bench.json)
+        k_mean = cpu["k_mean"] if cpu else 43.354429297893255
         flops_per_atom = FLOP_PER_TEST * N_POINTS * k_mean + FLOP_PER_PAIR * k_mean
         per_gpu_step_s = dev_ms_max * 1e-3 / args.steps
         traffic, traffic_info = ncu_traffic(args.structures)
