@@ -15,7 +15,9 @@
 // arithmetic below and of the reference's own dot product, and 100x smaller than a bin.
 #pragma once
 #include <cmath>
+#include <algorithm>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "sasa_device.cuh"
@@ -79,7 +81,9 @@ inline void cap_build_table(uint32_t n, const float *px, const float *py, const 
         lo[l] = l == 0 ? -INFINITY : -1.0 + 2.0 * (l - 1) / L;
         hi[l] = l == kCapLevels - 1 ? INFINITY : -1.0 + 2.0 * l / L;
     }
-    for (int iv = 0; iv < N; ++iv)
+    // rows of the direction grid are independent: spread them over the host threads (0.35 s single-threaded at 128 x 128 x 66)
+    auto rows = [&](int iv0, int iv1) {
+    for (int iv = iv0; iv < iv1; ++iv)
         for (int iu = 0; iu < N; ++iu) {
             const double u0 = -1.0 + 2.0 * iu / N, u1 = -1.0 + 2.0 * (iu + 1) / N;
             const double v0 = -1.0 + 2.0 * iv / N, v1 = -1.0 + 2.0 * (iv + 1) / N;
@@ -108,6 +112,12 @@ inline void cap_build_table(uint32_t n, const float *px, const float *py, const 
                 }
             }
         }
+    };
+    const int nt = std::max(1, std::min<int>((int)std::thread::hardware_concurrency(), 16));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(rows, N * t / nt, N * (t + 1) / nt);
+    rows(0, N / nt);
+    for (auto &th : pool) th.join();
 }
 
 // ---- device ------------------------------------------------------------------------------------------------------------
