@@ -118,12 +118,21 @@ def ncu_traffic(n_structures):
         return None, None
 
 
+def host_threads():
+    """Every host core this process may run on.  Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which would time the CPU arm on one thread at N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(data, seconds_target=15.0, threads=0):
     """Time the oracle's -O3 build (C restatement of RustSASA's CPU path, directory-mode threading: one structure
     per task over all host cores) on a bounded prefix of the batch.  Returns (atoms/s, info)."""
     from oracle import load
     fast = load(fast=True)
-    cores = threads or fast.max_threads()
+    cores = threads or host_threads()
     S = data.n_structures
     probe_n = min(S, max(2 * cores, 16))
     a1 = int(data.struct_off[probe_n])
@@ -162,7 +171,7 @@ def run_reference(args, rank):
     data = W.proteome_batch(args.structures)
     from oracle import load
     fast = load(fast=True)
-    cores = fast.max_threads()
+    cores = host_threads()
     # bounded sample per step so that (warmup + steps) stays within a few minutes
     info, _, (n, a1, g1) = cpu_sample(data, seconds_target=max(3.0, 60.0 / max(1, args.steps + args.warmup)))
     times = []
