@@ -49,6 +49,7 @@ struct SmallCfg {
 
 constexpr int kStreams = 3;
 constexpr size_t kChunkAtoms = 1000000;
+constexpr uint32_t kSingleLargeMin = 1024;   // atoms from which a lone structure takes the large-structure path
 
 }  // namespace
 
@@ -71,6 +72,12 @@ struct sasa_b200_ctx {
     // grow-only device arena for the host entry points
     void *arena = nullptr;
     size_t arena_bytes = 0;
+    // grow-only workspace of the large-structure path, shared by every batch of the context (a per-batch workspace cost
+    // nine cudaMalloc / cudaFree pairs per call: 6 ms for one 6,000-atom structure through calculate_sasa_internal).
+    // Uses on different streams are chained through ev_large.
+    LargeWorkspace large;
+    cudaEvent_t ev_large = nullptr;
+    bool large_used = false;
 };
 
 namespace {
@@ -202,6 +209,7 @@ struct sasa_b200_batch {
     sasa_b200_ctx *ctx = nullptr;
     size_t S = 0, n_atoms = 0, n_seg = 0;
     bool has_polar = false;
+    bool single_latency = false;   // one-structure convenience calls: prefer the multi-CTA large-structure path (see build_plan)
     std::vector<uint32_t> h_off;      // S+1
     std::vector<uint32_t> h_seg_off;  // S+1
     // two launch plans (without / with id classes: capacities differ)
@@ -215,7 +223,6 @@ struct sasa_b200_batch {
     uint32_t *d_off = nullptr, *d_seg_off = nullptr, *d_order[4] = {nullptr, nullptr, nullptr, nullptr}, *d_counters = nullptr;
     uint2 *d_seg_be = nullptr;
     uint8_t *d_polar = nullptr;
-    LargeWorkspace large;
     sasa_b200_stats last = {};
     uint32_t launches_last = 0;
 };
@@ -282,6 +289,10 @@ void build_plan(sasa_b200_batch *b, int variant) {
             const uint32_t n = b->h_off[i + 1] - b->h_off[i];
             size_t k = 0;
             while (k < cap.size() && n > cap[k]) ++k;
+            // A lone structure in a fused kernel occupies ONE SM (297 us per call at 1,283 atoms, 373 us at 2,622); the
+            // large-structure path spreads it over the GPU (171 us at 6,065 atoms, 264 us at 32,500).  Only the
+            // one-structure convenience entry points ask for this; explicit batches keep the fused kernels.
+            if (b->single_latency && b->S == 1 && n >= kSingleLargeMin) k = cap.size();
             bucket[k].push_back(i);
             if (k == cap.size()) b->max_large = std::max(b->max_large, n);
         }
@@ -404,9 +415,12 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
         kp.n_work = L.n_work;
         kp.work_counter = b->d_counters + L.counter;
         if (L.cfg < 0) {
-            int rc = large_enqueue(ctx->sm_count, b->large, kp, &b->h_order[variant][L.order_off], L.n_work,
+            if (ctx->large_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_large, 0));
+            int rc = large_enqueue(ctx->sm_count, ctx->large, kp, &b->h_order[variant][L.order_off], L.n_work,
                                    b->h_off.data(), st, launches);
             if (rc != 0) return fail(ctx, rc, "large-structure path failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_large, st));
+            ctx->large_used = true;
             continue;
         }
         const SmallCfg &c = ctx->cfgs[L.cfg];
@@ -503,6 +517,14 @@ int sasa_b200_create(int device, sasa_b200_ctx **out_ctx) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaEventCreate", e);
     }
     if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_large, cudaEventDisableTiming)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaEventCreate", e);
+    {   // per-batch topology arrays come from the stream-ordered pool: keep freed blocks cached instead of returning them
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if ((e = cudaMalloc(&ctx->d_err, sizeof(int))) != cudaSuccess) return bail(SASA_B200_ERR_OUT_OF_MEMORY, "cudaMalloc", e);
     if ((e = cudaMalloc(&ctx->d_stat, 3 * sizeof(unsigned long long))) != cudaSuccess) return bail(SASA_B200_ERR_OUT_OF_MEMORY, "cudaMalloc", e);
     cudaMemset(ctx->d_err, 0, sizeof(int));
@@ -529,6 +551,8 @@ void sasa_b200_destroy(sasa_b200_ctx *ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_large) cudaEventDestroy(ctx->ev_large);
+    large_release(ctx->large);
     cudaFree(ctx->d_err);
     cudaFree(ctx->d_stat);
     cudaFree(ctx->arena);
@@ -559,8 +583,9 @@ int sasa_b200_sphere_points(uint32_t n_points, float *xyz) {
     return SASA_B200_OK;
 }
 
-int sasa_b200_batch_create(sasa_b200_ctx *ctx, const uint64_t *struct_off, size_t S, const uint32_t *seg_be,
-                           const uint64_t *struct_seg_off, const uint8_t *seg_polar, sasa_b200_batch **out_batch) {
+static int batch_create_impl(sasa_b200_ctx *ctx, const uint64_t *struct_off, size_t S, const uint32_t *seg_be,
+                             const uint64_t *struct_seg_off, const uint8_t *seg_polar, sasa_b200_batch **out_batch,
+                             bool single_latency) {
     if (!ctx) return SASA_B200_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!out_batch || (!struct_off && S)) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "struct_off / out_batch is NULL");
@@ -575,6 +600,7 @@ int sasa_b200_batch_create(sasa_b200_ctx *ctx, const uint64_t *struct_off, size_
     sasa_b200_batch *b = new sasa_b200_batch();
     b->ctx = ctx;
     b->S = S;
+    b->single_latency = single_latency;
     b->h_off.resize(S + 1, 0);
     for (size_t i = 0; i <= S && S; ++i) b->h_off[i] = (uint32_t)struct_off[i];
     b->n_atoms = S ? b->h_off[S] : 0;
@@ -606,27 +632,31 @@ int sasa_b200_batch_create(sasa_b200_ctx *ctx, const uint64_t *struct_off, size_
             return cleanup(fail(ctx, e__ == cudaErrorMemoryAllocation ? SASA_B200_ERR_OUT_OF_MEMORY : SASA_B200_ERR_CUDA, \
                                 "%s failed: %s", #expr, cudaGetErrorString(e__)));                             \
     } while (0)
-    B_TRY(cudaMalloc(&b->d_off, (S + 1) * sizeof(uint32_t)));
-    B_TRY(cudaMemcpy(b->d_off, b->h_off.data(), (S + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    cudaStream_t ps = ctx->streams[0];
+    B_TRY(cudaSetDevice(ctx->device));
+    B_TRY(cudaMallocAsync(&b->d_off, (S + 1) * sizeof(uint32_t), ps));
+    B_TRY(cudaMemcpyAsync(b->d_off, b->h_off.data(), (S + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ps));
     for (int v = 0; v < 4; ++v) {
-        B_TRY(cudaMalloc(&b->d_order[v], std::max<size_t>(1, b->h_order[v].size()) * sizeof(uint32_t)));
+        B_TRY(cudaMallocAsync(&b->d_order[v], std::max<size_t>(1, b->h_order[v].size()) * sizeof(uint32_t), ps));
         if (!b->h_order[v].empty())
-            B_TRY(cudaMemcpy(b->d_order[v], b->h_order[v].data(), b->h_order[v].size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            B_TRY(cudaMemcpyAsync(b->d_order[v], b->h_order[v].data(), b->h_order[v].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ps));
     }
-    B_TRY(cudaMalloc(&b->d_counters, std::max<uint32_t>(1, *std::max_element(b->n_counters, b->n_counters + 4)) * sizeof(uint32_t)));
+    B_TRY(cudaMallocAsync(&b->d_counters, std::max<uint32_t>(1, *std::max_element(b->n_counters, b->n_counters + 4)) * sizeof(uint32_t), ps));
     if (b->n_seg) {
-        B_TRY(cudaMalloc(&b->d_seg_be, b->n_seg * sizeof(uint2)));
-        B_TRY(cudaMemcpy(b->d_seg_be, seg_be, b->n_seg * sizeof(uint2), cudaMemcpyHostToDevice));
-        B_TRY(cudaMalloc(&b->d_seg_off, (S + 1) * sizeof(uint32_t)));
-        B_TRY(cudaMemcpy(b->d_seg_off, b->h_seg_off.data(), (S + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        B_TRY(cudaMallocAsync(&b->d_seg_be, b->n_seg * sizeof(uint2), ps));
+        B_TRY(cudaMemcpyAsync(b->d_seg_be, seg_be, b->n_seg * sizeof(uint2), cudaMemcpyHostToDevice, ps));
+        B_TRY(cudaMallocAsync(&b->d_seg_off, (S + 1) * sizeof(uint32_t), ps));
+        B_TRY(cudaMemcpyAsync(b->d_seg_off, b->h_seg_off.data(), (S + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ps));
         if (seg_polar) {
-            B_TRY(cudaMalloc(&b->d_polar, b->n_seg));
-            B_TRY(cudaMemcpy(b->d_polar, seg_polar, b->n_seg, cudaMemcpyHostToDevice));
+            B_TRY(cudaMallocAsync(&b->d_polar, b->n_seg, ps));
+            B_TRY(cudaMemcpyAsync(b->d_polar, seg_polar, b->n_seg, cudaMemcpyHostToDevice, ps));
             b->has_polar = true;
         }
     }
-    if (b->max_large) {
-        int rc = large_reserve(b->large, b->max_large);
+    B_TRY(cudaStreamSynchronize(ps));   // the caller's arrays may go away; the topology is complete for any stream from here on
+    if (b->max_large) {   // (ctx->mu is held since the top of this function)
+        if (b->max_large > ctx->large.cap_atoms) cudaDeviceSynchronize();   // growing frees buffers a run in flight may still use
+        int rc = large_reserve(ctx->large, b->max_large);
         if (rc) return cleanup(fail(ctx, rc, "allocating the large-structure workspace (%u atoms) failed", b->max_large));
     }
 #undef B_TRY
@@ -634,17 +664,23 @@ int sasa_b200_batch_create(sasa_b200_ctx *ctx, const uint64_t *struct_off, size_
     return SASA_B200_OK;
 }
 
+int sasa_b200_batch_create(sasa_b200_ctx *ctx, const uint64_t *struct_off, size_t S, const uint32_t *seg_be,
+                           const uint64_t *struct_seg_off, const uint8_t *seg_polar, sasa_b200_batch **out_batch) {
+    return batch_create_impl(ctx, struct_off, S, seg_be, struct_seg_off, seg_polar, out_batch, false);
+}
+
 void sasa_b200_batch_destroy(sasa_b200_batch *b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(b->d_off);
-    cudaFree(b->d_seg_off);
-    for (int v = 0; v < 4; ++v) cudaFree(b->d_order[v]);
-    cudaFree(b->d_counters);
-    cudaFree(b->d_seg_be);
-    cudaFree(b->d_polar);
-    large_release(b->large);
+    cudaStream_t ps = b->ctx->streams[0];
+    if (b->d_off) cudaFreeAsync(b->d_off, ps);
+    if (b->d_seg_off) cudaFreeAsync(b->d_seg_off, ps);
+    for (int v = 0; v < 4; ++v)
+        if (b->d_order[v]) cudaFreeAsync(b->d_order[v], ps);
+    if (b->d_counters) cudaFreeAsync(b->d_counters, ps);
+    if (b->d_seg_be) cudaFreeAsync(b->d_seg_be, ps);
+    if (b->d_polar) cudaFreeAsync(b->d_polar, ps);
     delete b;
 }
 
@@ -822,7 +858,8 @@ static int run_atom_range_locked(sasa_b200_batch *b, const float *d_xyzr, const 
         return fail(ctx, SASA_B200_ERR_UNSUPPORTED, "statistics flags are not available in the atom-range split");
     uint32_t max_atoms = 0;
     for (size_t s = 0; s < b->S; ++s) max_atoms = std::max(max_atoms, b->h_off[s + 1] - b->h_off[s]);
-    if (max_atoms && (rc = large_reserve(b->large, max_atoms)) != 0)
+    if (max_atoms > ctx->large.cap_atoms) cudaDeviceSynchronize();
+    if (max_atoms && (rc = large_reserve(ctx->large, max_atoms)) != 0)
         return fail(ctx, rc, "allocating the large-structure workspace (%u atoms) failed", max_atoms);
     RunArgs ra;
     ra.d_xyzr = reinterpret_cast<const float4 *>(d_xyzr);
@@ -839,7 +876,12 @@ static int run_atom_range_locked(sasa_b200_batch *b, const float *d_xyzr, const 
     if (d_atom && b->n_atoms) CU_TRY(ctx, cudaMemsetAsync(d_atom, 0, b->n_atoms * sizeof(float), st));
     std::vector<uint32_t> order(b->S);
     std::iota(order.begin(), order.end(), 0u);
-    rc = large_enqueue(ctx->sm_count, b->large, kp, order.data(), (uint32_t)b->S, b->h_off.data(), st, &b->launches_last, rank, n_ranks);
+    if (ctx->large_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_large, 0));
+    rc = large_enqueue(ctx->sm_count, ctx->large, kp, order.data(), (uint32_t)b->S, b->h_off.data(), st, &b->launches_last, rank, n_ranks);
+    if (rc == 0) {
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_large, st));
+        ctx->large_used = true;
+    }
     if (rc != 0) return fail(ctx, rc, "large-structure path failed: %s", cudaGetErrorString(cudaGetLastError()));
     return SASA_B200_OK;
 }
@@ -921,7 +963,7 @@ int sasa_b200_run_batch(sasa_b200_ctx *ctx, const float *xyzr, const uint32_t *i
                         size_t S, const uint32_t *seg_be, const uint64_t *struct_seg_off, const uint8_t *seg_polar,
                         const sasa_b200_params *params, const sasa_b200_outputs *out, sasa_b200_stats *stats) {
     sasa_b200_batch *b = nullptr;
-    int rc = sasa_b200_batch_create(ctx, struct_off, S, seg_be, struct_seg_off, seg_polar, &b);
+    int rc = batch_create_impl(ctx, struct_off, S, seg_be, struct_seg_off, seg_polar, &b, S == 1);
     if (rc) return rc;
     rc = sasa_b200_batch_run_host(b, xyzr, id_class, params, out, stats);
     sasa_b200_batch_destroy(b);

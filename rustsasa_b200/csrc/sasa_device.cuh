@@ -19,7 +19,7 @@ constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kNbCap = 96;            // neighbour entries staged per warp (protein lists peak around 75)
 constexpr int kQueueCap = 128;        // survivor queue of one 128-point chunk (u16 per warp; aliases the candidate list)
-constexpr int kCandSlots = 2 * kQueueCap;   // u16 slots per warp: two candidate lists (the tight kernel keeps one atom's list alive while it gathers the next)
+constexpr int kCandSlots = kQueueCap;       // u16 slots of the per-warp candidate list
 constexpr int kListCap = 320;         // cell candidate positions cached per warp by the tight kernel (10 windows of 32)
 constexpr float kCutSlack = 1.0e-3f;  // Angstrom; keeps exactly-tangent pairs in the list
 constexpr float kCellSafety = 1.0002f;

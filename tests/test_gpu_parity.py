@@ -438,3 +438,41 @@ def test_sharded_run_matches_single(eng):
     assert np.array_equal(np.concatenate([p.counts for p in pieces]), whole.counts)
     assert np.array_equal(np.concatenate([p.seg_sasa for p in pieces]), whole.seg_sasa)
     assert np.array_equal(np.concatenate([p.protein for p in pieces]), whole.protein)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_cap_table_randomised_geometry(eng, oracle, seed):
+    """Stress of the cap-table occlusion (sasa_cap.cuh) away from protein statistics: random point counts <= 128 and lane
+    rules, probe radii 0..3 A, radii 0.4..3.2 A (cap levels from barely touching to a neighbour swallowing the atom),
+    densities from sparse gas to 3x protein density, coincident and nearly coincident centres (the degenerate bin), and
+    structures on both the fused and the large-structure path.  Counts must equal the oracle's EXACTLY: a table bin that
+    decided a point the reference's arithmetic decides differently would show up here."""
+    rng = np.random.default_rng(9000 + seed)
+    n_points = int(rng.choice([1, 5, 31, 32, 33, 64, 96, 100, 127, 128]))
+    lanes = int(rng.choice([4, 8, 16]))
+    probe = float(rng.choice([0.0, 0.3, 1.4, 2.2, 3.0]))
+    structs = []
+    for t in range(10):
+        n = int(rng.integers(1, 900))
+        density = float(rng.choice([0.005, 0.03, 0.057, 0.12, 0.17]))
+        side = (n / density) ** (1.0 / 3.0)
+        xyz = rng.uniform(0.0, side, size=(n, 3)) + rng.uniform(-300, 300, size=3)
+        rad = rng.uniform(0.4, 3.2, size=n) if t % 2 else rng.choice([1.42, 1.61, 1.76, 1.88], size=n)
+        if n > 20:   # coincident / nearly coincident centres and an atom inside a much larger one
+            xyz[1] = xyz[0]
+            xyz[3] = xyz[2] + 1e-4
+            xyz[5] = xyz[4] + [0.0, 0.0, 3e-4]
+            rad[7], xyz[7] = 3.2, xyz[6] + 0.2
+        structs.append(np.concatenate([xyz, rad[:, None]], axis=1).astype(np.float32))
+    big = rng.uniform(0.0, 95.0, size=(40000, 3))          # one structure for the large path (cap table on global atoms)
+    structs.append(np.concatenate([big, rng.uniform(1.2, 2.0, size=(40000, 1))], axis=1).astype(np.float32))
+    off = np.cumsum([0] + [s.shape[0] for s in structs]).astype(np.uint64)
+    xyzr = np.concatenate(structs)
+    b = eng.batch(off)
+    r = b.run_host(xyzr, probe_radius=probe, n_points=n_points, simd_lanes=lanes, want=("counts", "atom"))
+    for i, s in enumerate(structs):
+        o = oracle.calculate_sasa_internal(s, probe, n_points, lanes=lanes, threads=0 if s.shape[0] > 10000 else 1)
+        a0, a1 = int(off[i]), int(off[i + 1])
+        assert np.array_equal(r.counts[a0:a1], o["counts"]), (seed, i, n_points, lanes, probe)
+        assert np.array_equal(r.atom_sasa[a0:a1], o["sasa"]), (seed, i)
+    b.close()
