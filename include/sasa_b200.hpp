@@ -252,6 +252,9 @@ std::string sasa_result_to_xml(const SASAResult &result);    // quick_xml::se::t
 // vector, mismatched residue, negative or non-finite value).
 void sasa_result_to_protein_object(pdb::PDB &original_pdb, const SASAResult &result);
 
+// Optional: create the engine context and the per-n_points tables now (e.g. on a helper thread while files are parsed).
+void warm_up(const OptionValues &opt);
+
 // Engine selection for this process: CUDA device ordinal used by every call above (default: SASA_B200_DEVICE or 0).
 void set_device(int device);
 

@@ -7,10 +7,15 @@
 //   calculate_sasa_internal   src/lib.rs:249-298
 // The numeric part of process_atoms (sequential f32 sums per residue / chain / protein) runs on the GPU inside the
 // same launch (seg_sasa / protein outputs of sasa_b200_batch_run_host); strings and metadata stay here.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 
 #include "../../../include/sasa_b200.h"
 #include "../../../include/sasa_b200.hpp"
@@ -64,8 +69,14 @@ sasa_b200_ctx *context() {
     throw SASACalcError(SASACalcError::Kind::Device, std::string(what) + ": " + sasa_b200_last_error(ctx));
 }
 
-// Dense equality classes of the ids of one structure, or empty when all ids are distinct.
+// Dense equality classes of the ids of one structure, or empty when all ids are distinct (the usual case, decided by a
+// sort of a copy; the hash-map ranking only runs for files that really repeat an id, e.g. multi-model files).
 std::vector<std::uint32_t> id_classes(const std::vector<std::uint64_t> &ids, std::uint32_t base) {
+    {
+        std::vector<std::uint64_t> sorted(ids);
+        std::sort(sorted.begin(), sorted.end());
+        if (std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end()) return {};
+    }
     std::unordered_map<std::uint64_t, std::uint32_t> rank;
     rank.reserve(ids.size() * 2);
     std::vector<std::uint32_t> cls(ids.size());
@@ -74,7 +85,54 @@ std::vector<std::uint32_t> id_classes(const std::vector<std::uint64_t> &ids, std
     return cls;
 }
 
+// Host-side loops over the structures of a tile (packing, result assembly) on all cores.
+template <class F>
+void parallel_for(size_t n, F &&f) {
+    const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)std::min<size_t>(n / 64 + 1, 64)));
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; ++i) f(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; ++t)
+        pool.emplace_back([&] {
+            for (size_t i0; (i0 = next.fetch_add(32)) < n;)
+                for (size_t i = i0; i < std::min(n, i0 + 32); ++i) f(i);
+        });
+    for (auto &t : pool) t.join();
+}
+
+// Grow-only pinned staging buffer of this process (a cudaHostAlloc per tile cost tens of milliseconds).
+std::mutex g_pin_mu;
+void *g_pin = nullptr;
+size_t g_pin_bytes = 0;
+void *pinned_reserve(size_t bytes) {
+    if (bytes <= g_pin_bytes) return g_pin;
+    if (g_pin) sasa_b200_free_pinned(g_pin);
+    g_pin = nullptr;
+    g_pin_bytes = 0;
+    const size_t want = bytes + bytes / 4 + (1 << 20);
+    if (sasa_b200_alloc_pinned(want, &g_pin) != SASA_B200_OK) return nullptr;
+    g_pin_bytes = want;
+    return g_pin;
+}
+
 }  // namespace
+
+// Creates the engine context and the tables of this point count ahead of the first real call (CUDA context creation,
+// module load and the cap table are a few hundred milliseconds): the CLI runs this while it parses its first files.
+void warm_up(const OptionValues &opt) {
+    const bool trace = std::getenv("SASA_B200_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    sasa_b200_ctx *ctx = context();
+    if (trace) std::fprintf(stderr, "[sasa_b200] context created at %.3f s\n", since());
+    const float one[4] = {0.0f, 0.0f, 0.0f, 1.5f};
+    float out = 0.0f;
+    sasa_b200_calculate_sasa_internal(ctx, one, nullptr, 1, opt.probe_radius, opt.n_points, opt.threads, &out, nullptr);
+    if (trace) std::fprintf(stderr, "[sasa_b200] first call (point set, cap table, first launch) done at %.3f s\n", since());
+}
 
 void set_device(int device) {
     std::lock_guard<std::mutex> lk(g_ctx_mu);
@@ -172,7 +230,6 @@ Packed build_atoms_and_mapping(const pdb::PDB &pdb, LevelKind level, const Optio
 // ---- the batched engine call ----------------------------------------------------------------------------------------
 std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &packed, LevelKind level, const OptionValues &opt) {
     std::vector<ProcessOutcome> results;
-    results.reserve(packed.size());
     const size_t S = packed.size();
     std::vector<std::uint64_t> struct_off(S + 1, 0), seg_off(S + 1, 0);
     for (size_t s = 0; s < S; ++s) {
@@ -182,33 +239,35 @@ std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &pa
     const size_t N = struct_off[S], G = seg_off[S];
     sasa_b200_ctx *ctx = context();
     // pinned staging: the pipelined host entry point overlaps H2D, kernels and D2H across chunks
-    void *pin = nullptr;
+    std::lock_guard<std::mutex> pin_lock(g_pin_mu);   // one tile at a time owns the staging buffer
     const size_t in_bytes = N * 16, out_atom = level == LevelKind::Atom ? N * 4 : 0, out_seg = G * 4, out_prot = S * 12;
-    if (sasa_b200_alloc_pinned(in_bytes + out_atom + out_seg + out_prot + 64, &pin) != SASA_B200_OK) throw_device(nullptr, "alloc_pinned");
-    struct Free { void *p; ~Free() { sasa_b200_free_pinned(p); } } guard{pin};
+    void *pin = pinned_reserve(in_bytes + out_atom + out_seg + out_prot + 64);
+    if (!pin) throw_device(nullptr, "alloc_pinned");
     float *h_xyzr = static_cast<float *>(pin);
     float *h_atom = reinterpret_cast<float *>(static_cast<char *>(pin) + in_bytes);
     float *h_seg = reinterpret_cast<float *>(static_cast<char *>(pin) + in_bytes + out_atom);
     float *h_prot = reinterpret_cast<float *>(static_cast<char *>(pin) + in_bytes + out_atom + out_seg);
     std::vector<std::uint32_t> seg_be(2 * G), id_class;
     std::vector<std::uint8_t> polar(G);
-    bool any_dup = false;
-    for (size_t s = 0; s < S; ++s) {
+    std::vector<std::vector<std::uint32_t>> dup(S);   // per structure: id classes, empty when all ids are distinct
+    parallel_for(S, [&](size_t s) {
         const Packed &p = *packed[s];
         if (p.n_atoms()) std::memcpy(h_xyzr + 4 * struct_off[s], p.xyzr.data(), p.n_atoms() * 16);
         if (!p.seg_polar.empty()) {
             std::memcpy(seg_be.data() + 2 * seg_off[s], p.seg_be.data(), p.seg_be.size() * 4);
             std::memcpy(polar.data() + seg_off[s], p.seg_polar.data(), p.seg_polar.size());
         }
-        std::vector<std::uint32_t> cls = id_classes(p.ids, (std::uint32_t)struct_off[s]);
-        if (!cls.empty()) {
-            if (!any_dup) {   // first structure with duplicate ids: earlier atoms get distinct classes
-                id_class.resize(N);
-                for (size_t i = 0; i < N; ++i) id_class[i] = (std::uint32_t)i;
-                any_dup = true;
-            }
-            std::memcpy(id_class.data() + struct_off[s], cls.data(), cls.size() * 4);
+        dup[s] = id_classes(p.ids, (std::uint32_t)struct_off[s]);
+    });
+    bool any_dup = false;
+    for (size_t s = 0; s < S; ++s) {
+        if (dup[s].empty()) continue;
+        if (!any_dup) {   // first structure with duplicate ids: every other atom gets a class of its own
+            id_class.resize(N);
+            for (size_t i = 0; i < N; ++i) id_class[i] = (std::uint32_t)i;
+            any_dup = true;
         }
+        std::memcpy(id_class.data() + struct_off[s], dup[s].data(), dup[s].size() * 4);
     }
     sasa_b200_batch *batch = nullptr;
     if (sasa_b200_batch_create(ctx, struct_off.data(), S, G ? seg_be.data() : nullptr, G ? seg_off.data() : nullptr,
@@ -221,29 +280,30 @@ std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &pa
     const int rc = sasa_b200_batch_run_host(batch, h_xyzr, any_dup ? id_class.data() : nullptr, &prm, &outs, nullptr);
     sasa_b200_batch_destroy(batch);
     if (rc != SASA_B200_OK) throw_device(ctx, "batch_run_host");
-    for (size_t s = 0; s < S; ++s) {
+    results.assign(S, ProcessOutcome(SASAResult(std::vector<float>())));
+    parallel_for(S, [&](size_t s) {
         const Packed &p = *packed[s];
         switch (level) {
             case LevelKind::Atom:
-                results.emplace_back(SASAResult(std::vector<float>(h_atom + struct_off[s], h_atom + struct_off[s + 1])));
+                results[s] = SASAResult(std::vector<float>(h_atom + struct_off[s], h_atom + struct_off[s + 1]));
                 break;
             case LevelKind::Residue: {
                 std::vector<ResidueResult> v = p.residue_meta;
                 for (size_t k = 0; k < v.size(); ++k) v[k].value = h_seg[seg_off[s] + k];
-                results.emplace_back(SASAResult(std::move(v)));
+                results[s] = SASAResult(std::move(v));
                 break;
             }
             case LevelKind::Chain: {
                 std::vector<ChainResult> v = p.chain_meta;
                 for (size_t k = 0; k < v.size(); ++k) v[k].value = h_seg[seg_off[s] + k];
-                results.emplace_back(SASAResult(std::move(v)));
+                results[s] = SASAResult(std::move(v));
                 break;
             }
             case LevelKind::Protein:
-                results.emplace_back(SASAResult(ProteinResult{h_prot[3 * s], h_prot[3 * s + 1], h_prot[3 * s + 2]}));
+                results[s] = SASAResult(ProteinResult{h_prot[3 * s], h_prot[3 * s + 1], h_prot[3 * s + 2]});
                 break;
         }
-    }
+    });
     return results;
 }
 

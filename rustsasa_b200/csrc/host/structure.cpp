@@ -14,6 +14,8 @@
 // It is not a general structure parser (no symmetry, bonds or validation).
 #include <algorithm>
 #include <cctype>
+#include <charconv>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -179,7 +181,12 @@ const std::unordered_set<std::string> &elements() {
 
 // pdbtbx Atom::new: the element column if it names an element, else the atom name, else its first letter if CHNOS.
 std::string resolve_element(std::string_view element, std::string_view atom_name) {
-    const std::string e = upper(trim(element));
+    element = trim(element);
+    if (element.size() == 1) {   // the common case, no allocation: a one-letter symbol of the organic set
+        const char c = (char)std::toupper((unsigned char)element[0]);
+        if (std::strchr("CNOSHPFIBKVWYU", c)) return std::string(1, c);
+    }
+    const std::string e = upper(element);
     if (elements().count(e)) return e;
     const std::string n = upper(trim(atom_name));
     if (elements().count(n)) return n;
@@ -187,35 +194,67 @@ std::string resolve_element(std::string_view element, std::string_view atom_name
     return std::string();
 }
 
-void add_atom(Model &model, const std::string &chain_id, std::ptrdiff_t res_serial, const std::string &icode,
-              const std::string &res_name, const std::string &altloc, AtomRec &&atom) {
-    auto ci = model.chain_index.find(chain_id);
+// Where the previous atom went: consecutive atoms of a file almost always share chain, residue and conformer, so the
+// hash lookups (and the key strings they need) are only paid at the boundaries.
+struct AddCursor {
+    const Model *model = nullptr;
+    size_t chain = 0, residue = 0, conformer = 0;
+    std::ptrdiff_t res_serial = 0;
+    bool valid = false;
+};
+
+void add_atom(Model &model, std::string_view chain_id, std::ptrdiff_t res_serial, std::string_view icode,
+              std::string_view res_name, std::string_view altloc, AtomRec &&atom, AddCursor *cur = nullptr) {
+    if (cur && cur->valid && cur->model == &model && cur->res_serial == res_serial) {
+        Chain &chain = model.chains[cur->chain];
+        Residue &res = chain.residues[cur->residue];
+        Conformer &conf = res.conformers[cur->conformer];
+        if (chain.id == chain_id && res.icode == icode && conf.name == res_name && conf.altloc == altloc) {
+            conf.atoms.push_back(std::move(atom));
+            ++model.atom_count;
+            return;
+        }
+    }
+    const std::string chain_key(chain_id);
+    auto ci = model.chain_index.find(chain_key);
     if (ci == model.chain_index.end()) {
-        ci = model.chain_index.emplace(chain_id, model.chains.size()).first;
+        ci = model.chain_index.emplace(chain_key, model.chains.size()).first;
         model.chains.emplace_back();
-        model.chains.back().id = chain_id;
+        model.chains.back().id = chain_key;
+        model.chains.back().residue_index.reserve(1024);   // growth by rehashing was 8 rehashes per 500-residue chain
+        model.chains.back().residues.reserve(256);
     }
     Chain &chain = model.chains[ci->second];
-    const std::string rkey = std::to_string(res_serial) + "|" + icode;
+    std::string rkey = std::to_string(res_serial);
+    rkey += '|';
+    rkey += icode;
     auto ri = chain.residue_index.find(rkey);
     if (ri == chain.residue_index.end()) {
         ri = chain.residue_index.emplace(rkey, chain.residues.size()).first;
         chain.residues.emplace_back();
         chain.residues.back().serial = res_serial;
-        chain.residues.back().icode = icode;
+        chain.residues.back().icode = std::string(icode);
     }
     Residue &res = chain.residues[ri->second];
-    Conformer *conf = nullptr;
-    for (Conformer &c : res.conformers)
-        if (c.name == res_name && c.altloc == altloc) { conf = &c; break; }
-    if (!conf) {
+    size_t fi = res.conformers.size();
+    for (size_t i = 0; i < res.conformers.size(); ++i)
+        if (res.conformers[i].name == res_name && res.conformers[i].altloc == altloc) { fi = i; break; }
+    if (fi == res.conformers.size()) {
         res.conformers.emplace_back();
-        conf = &res.conformers.back();
-        conf->name = res_name;
-        conf->altloc = altloc;
+        res.conformers.back().name = std::string(res_name);
+        res.conformers.back().altloc = std::string(altloc);
+        res.conformers.back().atoms.reserve(16);   // one allocation per residue instead of four or five doublings
     }
-    conf->atoms.push_back(std::move(atom));
+    res.conformers[fi].atoms.push_back(std::move(atom));
     ++model.atom_count;
+    if (cur) {
+        cur->model = &model;
+        cur->chain = ci->second;
+        cur->residue = ri->second;
+        cur->conformer = fi;
+        cur->res_serial = res_serial;
+        cur->valid = true;
+    }
 }
 
 // pdbtbx/src/validate.rs:302-325: the blank-altloc conformer is removed and its atoms appended to every other one.
@@ -240,17 +279,27 @@ void reshuffle_conformers(PDB &pdb) {
             }
 }
 
+// strtol / strtod semantics on a trimmed field without the temporary string: an optional sign, then from_chars (which
+// rounds correctly, like Rust's str::parse the reference uses); anything from_chars cannot take falls back to strtod.
 long parse_long(std::string_view s, bool *ok = nullptr) {
-    std::string t(trim(s));
-    char *end = nullptr;
-    const long v = std::strtol(t.c_str(), &end, 10);
-    if (ok) *ok = !t.empty() && end && *end == '\0';
-    return v;
+    s = trim(s);
+    std::string_view t = s;
+    if (!t.empty() && t.front() == '+') t.remove_prefix(1);
+    long v = 0;
+    const auto r = std::from_chars(t.data(), t.data() + t.size(), v, 10);
+    if (ok) *ok = !s.empty() && r.ec == std::errc() && r.ptr == t.data() + t.size();
+    return r.ec == std::errc() ? v : 0;
 }
 
 double parse_double(std::string_view s) {
-    std::string t(trim(s));
-    return std::strtod(t.c_str(), nullptr);
+    s = trim(s);
+    std::string_view t = s;
+    if (!t.empty() && t.front() == '+') t.remove_prefix(1);
+    double v = 0.0;
+    const auto r = std::from_chars(t.data(), t.data() + t.size(), v, std::chars_format::general);
+    if (r.ec == std::errc() && r.ptr == t.data() + t.size()) return v;
+    const std::string tmp(s);
+    return std::strtod(tmp.c_str(), nullptr);
 }
 
 void flush_model(PDB &pdb, Model &model) {
@@ -259,62 +308,100 @@ void flush_model(PDB &pdb, Model &model) {
 
 }  // namespace
 
-PDB read_pdb(const std::string &path) {
-    std::ifstream fh(path);
+namespace {
+std::string read_file(const std::string &path) {
+    FILE *fh = std::fopen(path.c_str(), "rb");
     if (!fh) throw std::runtime_error("cannot open " + path);
+    std::string buf;
+    char chunk[1 << 16];
+    size_t n;
+    while ((n = std::fread(chunk, 1, sizeof chunk, fh)) > 0) buf.append(chunk, n);
+    std::fclose(fh);
+    return buf;
+}
+
+// Upper-cased, trimmed copy of a short fixed-width field into `out` (no heap: these fit the small-string buffer).
+void upper_trim(std::string_view f, std::string &out) {
+    f = trim(f);
+    out.assign(f);
+    for (char &c : out) c = (char)std::toupper((unsigned char)c);
+}
+}  // namespace
+
+PDB read_pdb(const std::string &path) {
+    const std::string text = read_file(path);
     PDB pdb;
     Model model;
+    AddCursor cur;
     long serial_add = 0, res_add = 0, last_serial = -1, last_res = -1;
     unsigned long long atom_id = 0;   // pdbtbx's id iterator (pdbtbx/src/read/pdb/parser.rs:116)
-    std::string line;
-    while (std::getline(fh, line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        const bool is_atom = line.compare(0, 6, "ATOM  ") == 0, is_het = line.compare(0, 6, "HETATM") == 0;
+    std::string name, resname;
+    char col[81];
+    size_t pos = 0;
+    while (pos < text.size()) {
+        size_t eol = text.find('\n', pos);
+        if (eol == std::string::npos) eol = text.size();
+        std::string_view raw(text.data() + pos, eol - pos);
+        pos = eol + 1;
+        if (!raw.empty() && raw.back() == '\r') raw.remove_suffix(1);
+        if (raw.size() < 6) continue;
+        const bool is_atom = raw.compare(0, 6, "ATOM  ") == 0, is_het = raw.compare(0, 6, "HETATM") == 0;
         if (is_atom || is_het) {
-            if (line.size() < 80) line.resize(80, ' ');
+            // the record as 80 columns, space-padded
+            const size_t len = std::min<size_t>(raw.size(), 80);
+            std::memcpy(col, raw.data(), len);
+            std::memset(col + len, ' ', 80 - len);
+            col[80] = 0;
+            const std::string_view line(col, 80);
             bool ok = false;
-            long serial = parse_long(std::string_view(line).substr(6, 5), &ok);
+            long serial = parse_long(line.substr(6, 5), &ok);
             if (!ok) serial = 0;
-            const std::string name = upper(trim(std::string_view(line).substr(12, 4)));
+            upper_trim(line.substr(12, 4), name);
             const char alt = line[16];
-            const std::string resname = upper(trim(std::string_view(line).substr(17, 3)));
+            upper_trim(line.substr(17, 3), resname);
             const char chain_c = line[21];
-            const long resseq = parse_long(std::string_view(line).substr(22, 4));
+            const long resseq = parse_long(line.substr(22, 4));
             const char icode = line[26];
-            const std::string_view occ_s = trim(std::string_view(line).substr(54, 6));
+            const std::string_view occ_s = trim(line.substr(54, 6));
             if (serial == 0 && last_serial == 99999) serial_add += 100000;
             if (resseq == 0 && last_res == 9999) res_add += 10000;
             AtomRec a;
             a.hetero = is_het;
             a.serial = (std::size_t)(serial + serial_add);
             a.name = name;
-            a.x = parse_double(std::string_view(line).substr(30, 8));
-            a.y = parse_double(std::string_view(line).substr(38, 8));
-            a.z = parse_double(std::string_view(line).substr(46, 8));
+            a.x = parse_double(line.substr(30, 8));
+            a.y = parse_double(line.substr(38, 8));
+            a.z = parse_double(line.substr(46, 8));
             a.occupancy = occ_s.empty() ? 1.0 : parse_double(occ_s);
             {
-                const std::string_view b_s = trim(std::string_view(line).substr(60, 6));
+                const std::string_view b_s = trim(line.substr(60, 6));
                 a.b_factor = b_s.empty() ? 0.0 : parse_double(b_s);
                 // columns 79-80: charge as digit + sign ("1+", "2-")
                 const char cd = line[78], cs = line[79];
                 if (cd >= '0' && cd <= '9' && (cs == '+' || cs == '-')) a.charge = (cs == '-' ? -1 : 1) * (cd - '0');
             }
-            a.element = resolve_element(std::string_view(line).substr(76, 2), name);
-            a.id = std::to_string(atom_id++);
-            add_atom(model, chain_c == ' ' ? std::string("A") : std::string(1, chain_c), resseq + res_add,
-                     icode == ' ' ? std::string() : std::string(1, icode), resname, alt == ' ' ? std::string() : std::string(1, alt),
-                     std::move(a));
+            a.element = resolve_element(line.substr(76, 2), name);
+            {
+                char idb[24];
+                const auto r = std::to_chars(idb, idb + sizeof idb, atom_id++);
+                a.id.assign(idb, r.ptr);
+            }
+            const char chain_s[1] = {chain_c == ' ' ? 'A' : chain_c};
+            add_atom(model, std::string_view(chain_s, 1), resseq + res_add, icode == ' ' ? std::string_view() : std::string_view(&line[26], 1),
+                     resname, alt == ' ' ? std::string_view() : std::string_view(&line[16], 1), std::move(a), &cur);
             last_serial = serial;
             last_res = resseq;
-        } else if (line.compare(0, 6, "MODEL ") == 0) {
+        } else if (raw.compare(0, 6, "MODEL ") == 0) {
             flush_model(pdb, model);
+            cur.valid = false;
             bool ok = false;
-            const long no = parse_long(std::string_view(line).substr(6), &ok);
+            const long no = parse_long(raw.substr(6), &ok);
             model = Model();
             model.serial = ok ? no : (long)pdb.models.size() + 1;
-        } else if (line.compare(0, 6, "ENDMDL") == 0) {
+        } else if (raw.compare(0, 6, "ENDMDL") == 0) {
             const std::ptrdiff_t next = model.serial + 1;
             flush_model(pdb, model);
+            cur.valid = false;
             model = Model();
             model.serial = next;
         }

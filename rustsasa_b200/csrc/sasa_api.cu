@@ -78,6 +78,7 @@ struct sasa_b200_ctx {
     LargeWorkspace large;
     cudaEvent_t ev_large = nullptr;
     bool large_used = false;
+    bool attr_done[8][6] = {};   // [kernel configuration][instantiation]: shared-memory attribute set (at first launch)
 };
 
 namespace {
@@ -176,11 +177,8 @@ int build_cfgs(sasa_b200_ctx *ctx) {
         if (c.cap[0] == 0 || c.cap[1] == 0 || std::max(c.smem[0], c.smem[1]) > ctx->smem_optin)
             return fail(ctx, SASA_B200_ERR_UNSUPPORTED, "the fused kernels are laid out for 228 KB of shared memory per SM (B200); this device offers %zu per block",
                         ctx->smem_optin);
-        for (int v = 0; v < 6; ++v) {
-            cudaError_t e = cudaFuncSetAttribute((const void *)pr.fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem[v & 1]);
-            if (e != cudaSuccess)
-                return fail(ctx, SASA_B200_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", c.smem[v & 1], cudaGetErrorString(e));
-        }
+        // (the MaxDynamicSharedMemorySize attribute is set at a kernel's first launch, enqueue_chunk: touching all thirty
+        // instantiations here made the driver load every one of them at context creation)
         ctx->cfgs.push_back(c);
     }
     if (ctx->cfgs.empty()) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "SASA_B200_CFGS selects no kernel configuration");
@@ -438,6 +436,12 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
         const bool tight = kp.n_points <= 128 && (kp.flags & 3u) == 0;
         const uint32_t body = std::min(kp.n_points, kp.n_body);
         const int which = (has_cls ? 1 : 0) + (tight ? (SASA_OPT_NSLT && body > 64 && body <= 96 ? 4 : 2) : 0);
+        if (!ctx->attr_done[c.proto][which]) {
+            cudaError_t ea = cudaFuncSetAttribute((const void *)kProtos[c.proto].fn[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ea != cudaSuccess)
+                return fail(ctx, SASA_B200_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%zu) failed: %s", smem, cudaGetErrorString(ea));
+            ctx->attr_done[c.proto][which] = true;
+        }
         cudaError_t e = cudaLaunchKernel((const void *)kProtos[c.proto].fn[which], dim3(grid), dim3(c.nt), args, smem, ls);
         if (e != cudaSuccess) return fail(ctx, SASA_B200_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
         if (ls != st) {
