@@ -413,9 +413,9 @@ PDB read_pdb(const std::string &path) {
 
 namespace {
 
-// One mmCIF data line -> tokens; quotes group, a quote only closes before whitespace or end of line.
-std::vector<std::string> cif_tokens(const std::string &line) {
-    std::vector<std::string> out;
+// One mmCIF data line -> tokens (views into the line); quotes group, a quote only closes before whitespace or end of line.
+void cif_tokens(std::string_view line, std::vector<std::string_view> &out) {
+    out.clear();
     size_t i = 0;
     const size_t n = line.size();
     while (i < n) {
@@ -425,86 +425,99 @@ std::vector<std::string> cif_tokens(const std::string &line) {
             const char q = line[i];
             size_t j = i + 1;
             while (j < n && !(line[j] == q && (j + 1 == n || std::isspace((unsigned char)line[j + 1])))) ++j;
-            out.emplace_back(line, i + 1, j - i - 1);
+            out.push_back(line.substr(i + 1, j - i - 1));
             i = j + 1;
         } else {
             size_t j = i;
             while (j < n && !std::isspace((unsigned char)line[j])) ++j;
-            out.emplace_back(line, i, j - i);
+            out.push_back(line.substr(i, j - i));
             i = j;
         }
     }
-    return out;
 }
 
 }  // namespace
 
 PDB read_mmcif(const std::string &path) {
-    std::ifstream fh(path);
-    if (!fh) throw std::runtime_error("cannot open " + path);
+    const std::string text = read_file(path);
     PDB pdb;
     std::unordered_map<long, size_t> model_index;
-    std::string line;
-    std::vector<std::string> lines;
-    while (std::getline(fh, line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        lines.push_back(line);
+    // the file as trimmed line views
+    std::vector<std::string_view> lines;
+    for (size_t pos = 0; pos < text.size();) {
+        size_t eol = text.find('\n', pos);
+        if (eol == std::string::npos) eol = text.size();
+        lines.push_back(trim(std::string_view(text.data() + pos, eol - pos)));
+        pos = eol + 1;
     }
     size_t i = 0;
     const size_t n = lines.size();
-    auto stripped = [&](size_t k) { return std::string(trim(lines[k])); };
+    auto is_site = [&](size_t k) { return lines[k].rfind("_atom_site.", 0) == 0; };
+    std::vector<std::string_view> tok;
+    std::string name, resname;
+    AddCursor cur;
     while (i < n) {
-        if (stripped(i) == "loop_" && i + 1 < n && stripped(i + 1).rfind("_atom_site.", 0) == 0) {
+        if (lines[i] == "loop_" && i + 1 < n && is_site(i + 1)) {
             ++i;
             std::unordered_map<std::string, int> col;
             int ncol = 0;
-            while (i < n && stripped(i).rfind("_atom_site.", 0) == 0) {
-                col[stripped(i).substr(11)] = ncol++;
+            while (i < n && is_site(i)) {
+                col[std::string(lines[i].substr(11))] = ncol++;
                 ++i;
             }
-            auto get = [&](const std::vector<std::string> &tok, const char *key) -> const std::string * {
-                auto it = col.find(key);
-                if (it == col.end()) return nullptr;
-                const std::string &v = tok[it->second];
-                return (v == "." || v == "?") ? nullptr : &v;
+            // the columns the path reads, resolved once (-1: absent)
+            auto idx = [&](const char *key) { auto it = col.find(key); return it == col.end() ? -1 : it->second; };
+            const int c_model = idx("pdbx_PDB_model_num"), c_group = idx("group_PDB"), c_atom = idx("label_atom_id"),
+                      c_comp = idx("label_comp_id"), c_aseq = idx("auth_seq_id"), c_lseq = idx("label_seq_id"),
+                      c_achain = idx("auth_asym_id"), c_lchain = idx("label_asym_id"), c_x = idx("Cartn_x"), c_y = idx("Cartn_y"),
+                      c_z = idx("Cartn_z"), c_occ = idx("occupancy"), c_b = idx("B_iso_or_equiv"), c_id = idx("id"),
+                      c_charge = idx("pdbx_formal_charge"), c_sym = idx("type_symbol"), c_icode = idx("pdbx_PDB_ins_code"),
+                      c_alt = idx("label_alt_id");
+            // value of a column, or nullptr-like empty optional when the column is absent or holds "." / "?"
+            auto get = [&](int c, std::string_view &v) {
+                if (c < 0) return false;
+                v = tok[(size_t)c];
+                return !(v == "." || v == "?");
             };
             while (i < n) {
-                const std::string s = stripped(i);
+                const std::string_view s = lines[i];
                 if (s.empty() || s[0] == '#' || s[0] == '_' || s == "loop_") break;
-                const std::vector<std::string> tok = cif_tokens(s);
+                cif_tokens(s, tok);
                 ++i;
                 if ((int)tok.size() < ncol) continue;
-                const std::string *v;
-                const long model_no = (v = get(tok, "pdbx_PDB_model_num")) ? parse_long(*v) : 1;
+                std::string_view v;
+                const long model_no = get(c_model, v) ? parse_long(v) : 1;
                 auto mi = model_index.find(model_no);
                 if (mi == model_index.end()) {
                     mi = model_index.emplace(model_no, pdb.models.size()).first;
                     pdb.models.emplace_back();
                     pdb.models.back().serial = model_no;
+                    cur.valid = false;   // the models vector may have moved
                 }
                 Model &model = pdb.models[mi->second];
-                const std::string group = (v = get(tok, "group_PDB")) ? *v : "ATOM";
-                const std::string name = (v = get(tok, "label_atom_id")) ? upper(*v) : "";
-                const std::string resname = (v = get(tok, "label_comp_id")) ? upper(*v) : "";
-                const std::string *seq = get(tok, "auth_seq_id");
-                if (!seq) seq = get(tok, "label_seq_id");
-                const std::string *chain = get(tok, "auth_asym_id");
-                if (!chain) chain = get(tok, "label_asym_id");
+                const bool hetero = get(c_group, v) && v == "HETATM";
+                if (get(c_atom, v)) upper_trim(v, name); else name.clear();
+                if (get(c_comp, v)) upper_trim(v, resname); else resname.clear();
+                std::string_view seq, chain, icode, alt;
+                const bool has_seq = get(c_aseq, seq) || get(c_lseq, seq);
+                const bool has_chain = get(c_achain, chain) || get(c_lchain, chain);
                 AtomRec a;
-                a.hetero = group == "HETATM";
+                a.hetero = hetero;
                 a.serial = model.atom_count;
                 a.name = name;
-                a.x = (v = get(tok, "Cartn_x")) ? parse_double(*v) : 0.0;
-                a.y = (v = get(tok, "Cartn_y")) ? parse_double(*v) : 0.0;
-                a.z = (v = get(tok, "Cartn_z")) ? parse_double(*v) : 0.0;
-                a.occupancy = (v = get(tok, "occupancy")) ? parse_double(*v) : 1.0;
-                a.b_factor = (v = get(tok, "B_iso_or_equiv")) ? parse_double(*v) : 0.0;
-                a.id = (v = get(tok, "id")) ? *v : std::to_string(model.atom_count);
-                if ((v = get(tok, "pdbx_formal_charge")) && !v->empty() && *v != "?" && *v != ".") a.charge = (int)parse_long(*v);
-                a.element = resolve_element((v = get(tok, "type_symbol")) ? *v : "", name);
-                const std::string *icode = get(tok, "pdbx_PDB_ins_code"), *alt = get(tok, "label_alt_id");
-                add_atom(model, chain ? *chain : std::string(), seq ? parse_long(*seq) : 0, icode ? *icode : std::string(), resname,
-                         alt ? *alt : std::string(), std::move(a));
+                a.x = get(c_x, v) ? parse_double(v) : 0.0;
+                a.y = get(c_y, v) ? parse_double(v) : 0.0;
+                a.z = get(c_z, v) ? parse_double(v) : 0.0;
+                a.occupancy = get(c_occ, v) ? parse_double(v) : 1.0;
+                a.b_factor = get(c_b, v) ? parse_double(v) : 0.0;
+                if (get(c_id, v)) a.id.assign(v);
+                else a.id = std::to_string(model.atom_count);
+                if (get(c_charge, v) && !v.empty()) a.charge = (int)parse_long(v);
+                a.element = resolve_element(get(c_sym, v) ? v : std::string_view(), name);
+                if (!get(c_icode, icode)) icode = std::string_view();
+                if (!get(c_alt, alt)) alt = std::string_view();
+                add_atom(model, has_chain ? chain : std::string_view(), has_seq ? parse_long(seq) : 0, icode, resname, alt, std::move(a),
+                         &cur);
             }
             continue;
         }
