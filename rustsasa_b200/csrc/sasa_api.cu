@@ -157,8 +157,11 @@ struct Proto {
               sasa_tight_kernel<NT, MINB, false, CMAX, 3>, sasa_tight_kernel<NT, MINB, true, CMAX, 3> } }
 // 0-2 keep 32 warps resident per SM (64 registers/thread); 3-4 keep 24 warps (85 registers/thread)
 #ifdef SASA_DEFAULT_PROTOS_ONLY   // quick builds of tuning variants: only the default configurations are instantiated
-const Proto kProtos[] = {SASA_PROTO(512, 2, 8192), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384),
-                         SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384)};
+#ifndef SASA_NT_MAIN
+#define SASA_NT_MAIN 1024
+#endif
+const Proto kProtos[] = {SASA_PROTO(512, 2, 8192), SASA_PROTO(512, 2, 8192), SASA_PROTO(SASA_NT_MAIN, 1, 16384),
+                         SASA_PROTO(512, 2, 8192), SASA_PROTO(SASA_NT_MAIN, 1, 16384)};
 #else
 const Proto kProtos[] = {SASA_PROTO(256, 4, 4096), SASA_PROTO(512, 2, 8192), SASA_PROTO(1024, 1, 16384),
                          SASA_PROTO(384, 2, 8192), SASA_PROTO(768, 1, 16384)};

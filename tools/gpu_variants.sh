@@ -8,9 +8,9 @@ mkdir -p $OUT
 for lib in rustsasa_b200/variants/*.so; do
     name=$(basename $lib .so); name=${name#libsasa_b200_}
     export SASA_B200_LIB=$PWD/$lib
-    line=$(timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu 2> $OUT/$name.err | tail -1)
+    line=$(timeout 120 python bench.py --steps 6 --warmup 3 --no-cpu 2> $OUT/$name.err | tail -1)
     echo "$line" > $OUT/$name.json
-    timeout 300 ncu --metrics smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum \
+    timeout 120 ncu --metrics smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum \
         --clock-control none -k regex:sasa_tight_kernel -s 3 -c 1 --csv --log-file $OUT/$name.ncu.csv \
         python bench.py --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1
     python - "$name" "$OUT/$name.json" "$OUT/$name.ncu.csv" <<'PY'
