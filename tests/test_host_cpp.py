@@ -272,3 +272,22 @@ def test_writeback_on_altloc_and_multimodel_files(host):
         if n_all > 1:
             with pytest.raises(host.HostError):
                 host.writeback(path, "atom", vals[:-1])
+
+
+def test_number_fields_parse_like_the_mirror(host, tmp_path):
+    """The allocation-free field parser (from_chars + fallbacks) against the Python mirror's float(): explicit '+' signs,
+    exponents, missing occupancy / B-factor columns, short lines, CRLF line ends, serial / residue-number wrap-around."""
+    lines = [
+        "ATOM      1  N   ALA A   1     +20.154 -16.967  2.5e+1  1.00 10.00           N",
+        "ATOM      2  CA  ALA A   1      19.030  16.155  25.000",
+        "ATOM  99999  C   ALA A9999      17.948  16.712  25.000  0.50               C",
+        "ATOM      0  O   ALA A   0      16.500  17.000  25.000  1.00  0.00           O",
+        "HETATM    1  O   HOH A   1      1.0e1   +.5     -0.     1.00  0.00           O",
+    ]
+    f = tmp_path / "n.pdb"
+    f.write_bytes(("\r\n".join(lines) + "\r\nEND\r\n").encode())
+    for level in ("atom", "residue", "protein"):
+        got = check_same(host, str(f), level, include_hetatms=True, allow_vdw_fallback=True)
+        assert got is not None and got["xyzr"].shape[0] == 5
+    got = host.pack(str(f), "atom", include_hetatms=True, allow_vdw_fallback=True)
+    assert np.allclose(got["xyzr"][0, :3], [20.154, -16.967, 25.0]) and np.allclose(got["xyzr"][4, :3], [10.0, 0.5, 0.0])
