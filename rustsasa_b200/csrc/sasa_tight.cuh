@@ -6,17 +6,20 @@
 // shared memory instead of unrolled register windows, the tile routine takes its shape at run time, and the
 // never-taken fallbacks (dense clusters) sit behind one __noinline__ call.
 //
-// Per cell (one warp owns a run of consecutive cells):
+// Per cell (warps claim runs of the cell-sorted atom order, snapped to whole cells):
 //   list     the (2e+1)^2 cell rows around the cell are contiguous ranges of the cell-sorted atom array; their
 //            positions are flattened once into a per-warp u16 list, padded to a multiple of 32 with the
 //            far-away sentinel atom
 // Per atom of the cell:
 //   gather   32 listed candidates per step: distance test, ballot, compaction into a u16 neighbour list
+//   cap      the cap-table occlusion of sasa_cap.cuh (default): one lane per neighbour, table masks, exact ring tests
+// or, with -DSASA_OPT_CAP=0, the earlier two-phase point tests:
 //   entries  (vx, vy, vz, limit) per neighbour with the reference's arithmetic, "near" neighbours first
 //   phase 1  all body points (3 slots per lane for n = 100) against the first m entries:
 //            one broadcast LDS.128 + 3 x (FMUL, 2 FFMA, FSETP.LT.OR) per entry
 //   phase 2  the surviving points against the remaining entries as a G x (32/G) tile of (survivor, entry) pairs
 //   tail     the n mod lanes tail points (unfused dot, <=) against all entries, same tile form
+// Between structures: warp 0 claims the CTA's next structure early and prefetches its atoms into L2.
 #pragma once
 #include "sasa_cap.cuh"
 #include "sasa_small.cuh"
@@ -47,8 +50,8 @@ namespace sasa {
 #define SASA_OPT_GU 2         // gather: 32-candidate steps per unrolled trip
 #endif
 #ifndef SASA_OPT_AREA
-#define SASA_OPT_AREA 0       // the per-atom phase stores areas (and writes counts straight to global memory): the output
-                              // stage needs no second read of the radii
+#define SASA_OPT_AREA 0       // 1: the per-atom phase stores areas (and writes counts straight to global memory) so that the
+                              // output stage needs no second read of the radii -- measured 1 % slower (lane-0 work), off
 #endif
 #ifndef SASA_OPT_ACLAIM
 #define SASA_OPT_ACLAIM 4     // > 0: warps claim runs of ATOMS (at least this many) of the cell-sorted order instead of runs
@@ -59,7 +62,7 @@ namespace sasa {
                               // the cell's first atom, so no candidate list is built twice
 #endif
 #ifndef SASA_OPT_GRIDLD
-#define SASA_OPT_GRIDLD 0     // the grid is re-read from shared memory at every cell instead of living in (spilled) registers
+#define SASA_OPT_GRIDLD 0     // 1: the grid is re-read from shared memory at every cell instead of living in registers (-1 %)
 #endif
 #ifndef SASA_OPT_NEXT
 #define SASA_OPT_NEXT 1       // warp 0 claims the CTA's next structure and prefetches its atoms into L2 while the other
@@ -358,11 +361,12 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
 #endif
         if (!ok) continue;
 
-        // ---- per-atom work: warps claim runs of consecutive cells; the atoms of a cell share its candidate list ----
+        // ---- per-atom work: warps claim runs of the cell-sorted atom order, whole cells at a time; the atoms of a cell
+        // share its candidate list ----
         unsigned pairs = 0;   // neighbour pairs seen by this warp (statistics; the cold path counts into misc[6] itself)
         for (;;) {
-            // guided self-scheduling: long runs of cells while plenty remain, short ones near the end of the structure
-            // (any positive increment partitions the cells, so the stale read of the counter is harmless)
+            // guided self-scheduling: long runs while plenty remain, short ones near the end of the structure
+            // (any positive increment partitions the range, so the stale read of the counter is harmless)
             int c0 = 0, take = 0;
 #if SASA_OPT_ACLAIM > 0
             if (lane == 0) {
@@ -402,8 +406,8 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
             }
 #endif
             while (pos < pos_end) {
-                // the cell of atom `pos` and the end of its run in the sorted array (the grid is re-read from shared memory
-                // at every cell instead of pinning -- in practice spilling -- 8 registers through the loop)
+                // the cell of atom `pos` and the end of its run in the sorted array (SASA_OPT_GRIDLD: the grid re-read from
+                // shared memory at every cell instead of held in registers -- measured 1 % slower, off)
 #if SASA_OPT_GRIDLD
                 const Grid g = load_grid(V.misc);
 #else
