@@ -155,8 +155,8 @@ __device__ __forceinline__ void stage_points(const KParams &p, float4 *ptab) {
     }
 }
 
-// The structure's cell grid parked in misc[8..15]: the tight kernel re-reads it at every cell instead of keeping it in
-// registers (volatile: the loads must stay where they are written).
+// The structure's cell grid parked in misc[8..15] for code that would rather re-read it than hold eight registers (the
+// tight kernel's cold-path experiments, SASA_OPT_GRIDLD; volatile: the loads must stay where they are written).
 __device__ __forceinline__ void store_grid(int *misc, const Grid &g) {
     misc[8] = __float_as_int(g.minx); misc[9] = __float_as_int(g.miny); misc[10] = __float_as_int(g.minz);
     misc[11] = __float_as_int(g.inv_c); misc[12] = g.nx; misc[13] = g.ny; misc[14] = g.nz; misc[15] = g.e;
