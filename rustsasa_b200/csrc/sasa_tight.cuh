@@ -50,7 +50,7 @@ namespace sasa {
 #define SASA_OPT_GU 2         // gather: 32-candidate steps per unrolled trip
 #endif
 #ifndef SASA_OPT_G2
-#define SASA_OPT_G2 1         // gather: explicit two-step trips with the loads of both steps ahead of the stores
+#define SASA_OPT_G2 2         // gather: explicit G-step trips with the loads of all G steps ahead of the stores (0: plain loop)
 #endif
 #ifndef SASA_OPT_AREA
 #define SASA_OPT_AREA 0       // 1: the per-atom phase stores areas (and writes counts straight to global memory) so that the
@@ -131,29 +131,39 @@ __device__ __forceinline__ int tight_gather(const float4 *s_atom, const uint32_t
     const uint32_t cls_i = HAS_CLS ? s_cls[pos] : 0u;
     int k = 0;
 #if SASA_OPT_G2
-    // two steps per trip with every load ahead of the first store, so that the two dependent shared-memory round trips
-    // (list entry -> atom) of both steps overlap
+    // G steps per trip with every load ahead of the first store, so that the dependent shared-memory round trips
+    // (list entry -> atom) of all G steps overlap
+    constexpr int G = SASA_OPT_G2 < 2 ? 2 : SASA_OPT_G2;
     int w0 = 0;
 #pragma unroll 1
-    for (; w0 + 32 < total; w0 += 64) {
-        const int j0 = (int)list[w0 + lane], j1 = (int)list[w0 + 32 + lane];
-        const float4 b0 = s_atom[j0], b1 = s_atom[j1];
-        const float dx0 = ai.x - b0.x, dy0 = ai.y - b0.y, dz0 = ai.z - b0.z;
-        const float dx1 = ai.x - b1.x, dy1 = ai.y - b1.y, dz1 = ai.z - b1.z;
-        const float d20 = fmaf(dx0, dx0, fmaf(dy0, dy0, dz0 * dz0)), d21 = fmaf(dx1, dx1, fmaf(dy1, dy1, dz1 * dz1));
-        const float c0 = reach_i + b0.w, c1 = reach_i + b1.w;
-        bool acc0 = (d20 <= c0 * c0) & (j0 != pos), acc1 = (d21 <= c1 * c1) & (j1 != pos);
-        if (HAS_CLS) {
-            acc0 = acc0 && (s_cls[j0] != cls_i);
-            acc1 = acc1 && (s_cls[j1] != cls_i);
+    for (; w0 + 32 * (G - 1) < total; w0 += 32 * G) {
+        int j[G];
+        float4 b[G];
+        bool acc[G];
+        unsigned m[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) j[g] = (int)list[w0 + 32 * g + lane];
+#pragma unroll
+        for (int g = 0; g < G; ++g) b[g] = s_atom[j[g]];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float dx = ai.x - b[g].x, dy = ai.y - b[g].y, dz = ai.z - b[g].z;
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            const float cut = reach_i + b[g].w;
+            acc[g] = (d2 <= cut * cut) & (j[g] != pos);          // sentinel pads fail the distance test
+            if (HAS_CLS) acc[g] = acc[g] && (s_cls[j[g]] != cls_i);   // (the sentinel slot of s_cls is never read)
         }
-        const unsigned m0 = __ballot_sync(kFull, acc0), m1 = __ballot_sync(kFull, acc1);
-        const int at0 = k + __popc(m0 & lt), at1 = k + __popc(m0) + __popc(m1 & lt);
-        if (acc0 & (at0 < kQueueCap)) cand[at0] = (uint16_t)j0;
-        if (acc1 & (at1 < kQueueCap)) cand[at1] = (uint16_t)j1;
-        k += __popc(m0) + __popc(m1);
+#pragma unroll
+        for (int g = 0; g < G; ++g) m[g] = __ballot_sync(kFull, acc[g]);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int at = k + __popc(m[g] & lt);
+            if (acc[g] & (at < kQueueCap)) cand[at] = (uint16_t)j[g];
+            k += __popc(m[g]);
+        }
     }
-    if (w0 < total) {
+#pragma unroll 1
+    for (; w0 < total; w0 += 32) {
         const int j = (int)list[w0 + lane];
         const float4 aj = s_atom[j];
         const float dx = ai.x - aj.x, dy = ai.y - aj.y, dz = ai.z - aj.z;
