@@ -76,11 +76,23 @@ HOST_API long sasa_b200_host_process_json(const char *path, int level, float pro
     return -1;
 }
 
-// writers on hand-made values (CPU-only formatting tests): kind 0 atom, 3 protein
+// writers on hand-made values (CPU-only formatting tests): kind 0 atom, 1 residue, 2 chain, 3 protein
 HOST_API long sasa_b200_host_format(int xml, int kind, const float *values, size_t n, char *out, size_t outlen) {
     SASAResult r;
-    if (kind == 3 && n >= 3) r = ProteinResult{values[0], values[1], values[2]};
-    else r = std::vector<float>(values, values + n);
+    if (kind == 3 && n >= 3) {
+        r = ProteinResult{values[0], values[1], values[2]};
+    } else if (kind == 1) {   // residues with made-up metadata: serial i + 1, every third one polar SER with insertion code "B"
+        std::vector<ResidueResult> v;
+        for (size_t i = 0; i < n; ++i)
+            v.push_back(ResidueResult{(std::ptrdiff_t)i + 1, i % 3 == 2 ? "B" : "", values[i], i % 3 == 2 ? "SER" : "MET", i % 3 == 2, "A"});
+        r = std::move(v);
+    } else if (kind == 2) {
+        std::vector<ChainResult> v;
+        for (size_t i = 0; i < n; ++i) v.push_back(ChainResult{std::string(1, (char)('A' + i % 26)), values[i]});
+        r = std::move(v);
+    } else {
+        r = std::vector<float>(values, values + n);
+    }
     const std::string s = xml ? sasa_result_to_xml(r) : sasa_result_to_json(r);
     if (s.size() + 1 > outlen) return -1;
     std::memcpy(out, s.c_str(), s.size() + 1);

@@ -291,3 +291,18 @@ def test_number_fields_parse_like_the_mirror(host, tmp_path):
         assert got is not None and got["xyzr"].shape[0] == 5
     got = host.pack(str(f), "atom", include_hetatms=True, allow_vdw_fallback=True)
     assert np.allclose(got["xyzr"][0, :3], [20.154, -16.967, 25.0]) and np.allclose(got["xyzr"][4, :3], [10.0, 0.5, 0.0])
+
+
+def test_residue_and_chain_json_shape(host):
+    """serde's externally tagged enum with the struct fields in declaration order (src/structures/atomic.rs:26-70,
+    SURVEY.md 8f row f-3)."""
+    js = host.format_values([25.0, 0.5, 101.25], kind="residue")
+    assert js == ('{"Residue":[{"serial_number":1,"insertion_code":"","value":25.0,"name":"MET","is_polar":false,"chain_id":"A"},'
+                  '{"serial_number":2,"insertion_code":"","value":0.5,"name":"MET","is_polar":false,"chain_id":"A"},'
+                  '{"serial_number":3,"insertion_code":"B","value":101.25,"name":"SER","is_polar":true,"chain_id":"A"}]}')
+    assert host.format_values([1.5, 2.0], kind="chain") == '{"Chain":[{"name":"A","value":1.5},{"name":"B","value":2.0}]}'
+    rng = np.random.default_rng(1)
+    v = (rng.random(700) * 300).astype(np.float32)
+    back = json.loads(host.format_values(v, kind="residue"))["Residue"]
+    assert [r["serial_number"] for r in back] == list(range(1, 701))
+    assert np.array_equal(np.array([r["value"] for r in back], np.float32), v)
