@@ -338,6 +338,11 @@ PDB read_pdb(const std::string &path) {
     AddCursor cur;
     long serial_add = 0, res_add = 0, last_serial = -1, last_res = -1;
     unsigned long long atom_id = 0;   // pdbtbx's id iterator (pdbtbx/src/read/pdb/parser.rs:116)
+    // blank chain IDs take the letter of an 'A'..'Z' cycle that advances on every TER record and is never reset, not even
+    // by MODEL (pdbtbx/src/read/pdb/parser.rs:113-115, :176-180, :511): TER-separated chains without IDs (typical MD
+    // output) become chains A, B, C, ...
+    int chain_letter = 0;
+    std::ptrdiff_t model_no = 0;      // number of the last MODEL record (0 without one), parser.rs:98, :305
     std::string name, resname;
     char col[81];
     size_t pos = 0;
@@ -347,7 +352,10 @@ PDB read_pdb(const std::string &path) {
         std::string_view raw(text.data() + pos, eol - pos);
         pos = eol + 1;
         if (!raw.empty() && raw.back() == '\r') raw.remove_suffix(1);
-        if (raw.size() < 6) continue;
+        if (raw.size() <= 6) {   // short lines: only TER counts (pdbtbx lexer.rs:87-91)
+            if (raw.size() > 2 && raw.compare(0, 3, "TER") == 0) chain_letter = (chain_letter + 1) % 26;
+            continue;
+        }
         const bool is_atom = raw.compare(0, 6, "ATOM  ") == 0, is_het = raw.compare(0, 6, "HETATM") == 0;
         if (is_atom || is_het) {
             // the record as 80 columns, space-padded
@@ -389,26 +397,31 @@ PDB read_pdb(const std::string &path) {
                 const auto r = std::to_chars(idb, idb + sizeof idb, atom_id++);
                 a.id.assign(idb, r.ptr);
             }
-            const char chain_s[1] = {chain_c == ' ' ? 'A' : chain_c};
+            const char chain_s[1] = {is_space(chain_c) ? (char)('A' + chain_letter) : chain_c};
             add_atom(model, std::string_view(chain_s, 1), resseq + res_add, icode == ' ' ? std::string_view() : std::string_view(&line[26], 1),
                      resname, alt == ' ' ? std::string_view() : std::string_view(&line[16], 1), std::move(a), &cur);
             last_serial = serial;
             last_res = resseq;
         } else if (raw.compare(0, 6, "MODEL ") == 0) {
+            // the model in progress is closed by the NEXT MODEL record (or MASTER, or the end of the file), not by ENDMDL,
+            // which pdbtbx ignores (parser.rs:282-306, lexer.rs:82): atoms between ENDMDL and MODEL stay in the old model
+            model.serial = model_no;
             flush_model(pdb, model);
             cur.valid = false;
             bool ok = false;
             const long no = parse_long(raw.substr(6), &ok);
+            model_no = ok ? no : 0;
             model = Model();
-            model.serial = ok ? no : (long)pdb.models.size() + 1;
-        } else if (raw.compare(0, 6, "ENDMDL") == 0) {
-            const std::ptrdiff_t next = model.serial + 1;
-            flush_model(pdb, model);
+        } else if (raw.compare(0, 6, "MASTER") == 0) {
+            model.serial = model_no;
+            flush_model(pdb, model);   // parser.rs:435-456
             cur.valid = false;
             model = Model();
-            model.serial = next;
+        } else if (raw.compare(0, 6, "TER   ") == 0) {
+            chain_letter = (chain_letter + 1) % 26;   // lexer.rs:83, :89; parser.rs:511
         }
     }
+    model.serial = model_no;
     flush_model(pdb, model);
     reshuffle_conformers(pdb);
     return pdb;
@@ -416,27 +429,61 @@ PDB read_pdb(const std::string &path) {
 
 namespace {
 
-// One mmCIF data line -> tokens (views into the line); quotes group, a quote only closes before whitespace or end of line.
-void cif_tokens(std::string_view line, std::vector<std::string_view> &out) {
-    out.clear();
-    size_t i = 0;
-    const size_t n = line.size();
-    while (i < n) {
-        while (i < n && std::isspace((unsigned char)line[i])) ++i;
-        if (i >= n) break;
-        if (line[i] == '\'' || line[i] == '"') {
-            const char q = line[i];
-            size_t j = i + 1;
-            while (j < n && !(line[j] == q && (j + 1 == n || std::isspace((unsigned char)line[j + 1])))) ++j;
-            out.push_back(line.substr(i + 1, j - i - 1));
-            i = j + 1;
-        } else {
-            size_t j = i;
-            while (j < n && !std::isspace((unsigned char)line[j])) ++j;
-            out.push_back(line.substr(i, j - i));
-            i = j;
+// Next token of a CIF text at or after p (STAR tokenisation as far as _atom_site needs it): whitespace separates tokens,
+// '#' at a token start comments out the rest of the line, a quote only closes before whitespace or the end of the text,
+// and a ';' in the first column opens a text field that runs to the next line starting with ';'.  `bare` tells an
+// unquoted token (which may be a tag or a keyword) from a quoted value.  Returns false at the end of the text.
+bool cif_next(const char *&p, const char *const begin, const char *const end, std::string_view &tok, bool &bare) {
+    for (;;) {
+        while (p < end && is_space(*p)) ++p;
+        if (p >= end) return false;
+        if (*p == '#') {
+            while (p < end && *p != '\n') ++p;
+            continue;
         }
+        break;
     }
+    if (*p == ';' && (p == begin || p[-1] == '\n')) {
+        const char *q = p + 1;
+        const char *stop = q;
+        for (;;) {   // the closing ';' is the first character of a line
+            while (stop < end && *stop != '\n') ++stop;
+            if (stop >= end || (stop + 1 < end && stop[1] == ';')) break;
+            ++stop;
+        }
+        tok = trim(std::string_view(q, (size_t)(stop - q)));
+        p = stop + 2 <= end ? stop + 2 : end;
+        bare = false;
+        return true;
+    }
+    if (*p == '\'' || *p == '"') {
+        const char qc = *p;
+        const char *q = p + 1;
+        while (q < end && !(*q == qc && (q + 1 == end || is_space(q[1]))) && *q != '\n') ++q;
+        tok = std::string_view(p + 1, (size_t)(q - p - 1));
+        p = q < end && *q == qc ? q + 1 : q;
+        bare = false;
+        return true;
+    }
+    const char *q = p;
+    while (q < end && !is_space(*q)) ++q;
+    tok = std::string_view(p, (size_t)(q - p));
+    p = q;
+    bare = true;
+    return true;
+}
+
+bool cif_ends_loop(std::string_view t) {
+    if (t.empty()) return false;
+    if (t[0] == '_') return true;
+    auto starts = [&](const char *kw) {
+        const size_t n = std::strlen(kw);
+        if (t.size() < n) return false;
+        for (size_t i = 0; i < n; ++i)
+            if (std::tolower((unsigned char)t[i]) != kw[i]) return false;
+        return true;
+    };
+    return starts("loop_") || starts("data_") || starts("save_") || starts("global_") || starts("stop_");
 }
 
 }  // namespace
@@ -445,49 +492,53 @@ PDB read_mmcif(const std::string &path) {
     const std::string text = read_file(path);
     PDB pdb;
     std::unordered_map<long, size_t> model_index;
-    // the file as trimmed line views
-    std::vector<std::string_view> lines;
-    for (size_t pos = 0; pos < text.size();) {
-        size_t eol = text.find('\n', pos);
-        if (eol == std::string::npos) eol = text.size();
-        lines.push_back(trim(std::string_view(text.data() + pos, eol - pos)));
-        pos = eol + 1;
-    }
-    size_t i = 0;
-    const size_t n = lines.size();
-    auto is_site = [&](size_t k) { return lines[k].rfind("_atom_site.", 0) == 0; };
+    const char *const begin = text.data(), *const end = text.data() + text.size();
     std::vector<std::string_view> tok;
     std::string name, resname;
     AddCursor cur;
-    while (i < n) {
-        if (lines[i] == "loop_" && i + 1 < n && is_site(i + 1)) {
-            ++i;
-            std::unordered_map<std::string, int> col;
-            int ncol = 0;
-            while (i < n && is_site(i)) {
-                col[std::string(lines[i].substr(11))] = ncol++;
-                ++i;
+    const char *p = begin;
+    std::string_view t;
+    bool bare = false;
+    bool have = cif_next(p, begin, end, t, bare);
+    while (have) {
+        if (!(bare && t.size() == 5 && cif_ends_loop(t) && t[4] == '_')) {   // not "loop_"
+            have = cif_next(p, begin, end, t, bare);
+            continue;
+        }
+        // a loop: its tags, then -- for _atom_site -- its values as a token stream (rows may wrap across lines and hold
+        // quoted or ';' text values; pdbtbx parses loops token-wise too, pdbtbx/src/read/mmcif/lexer.rs)
+        std::unordered_map<std::string, int> col;
+        int ncol = 0;
+        bool site = false;
+        have = cif_next(p, begin, end, t, bare);
+        while (have && bare && !t.empty() && t[0] == '_') {
+            if (t.rfind("_atom_site.", 0) == 0) {
+                site = true;
+                col[std::string(t.substr(11))] = ncol;
             }
-            // the columns the path reads, resolved once (-1: absent)
-            auto idx = [&](const char *key) { auto it = col.find(key); return it == col.end() ? -1 : it->second; };
-            const int c_model = idx("pdbx_PDB_model_num"), c_group = idx("group_PDB"), c_atom = idx("label_atom_id"),
-                      c_comp = idx("label_comp_id"), c_aseq = idx("auth_seq_id"), c_lseq = idx("label_seq_id"),
-                      c_achain = idx("auth_asym_id"), c_lchain = idx("label_asym_id"), c_x = idx("Cartn_x"), c_y = idx("Cartn_y"),
-                      c_z = idx("Cartn_z"), c_occ = idx("occupancy"), c_b = idx("B_iso_or_equiv"), c_id = idx("id"),
-                      c_charge = idx("pdbx_formal_charge"), c_sym = idx("type_symbol"), c_icode = idx("pdbx_PDB_ins_code"),
-                      c_alt = idx("label_alt_id");
-            // value of a column, or nullptr-like empty optional when the column is absent or holds "." / "?"
-            auto get = [&](int c, std::string_view &v) {
-                if (c < 0) return false;
-                v = tok[(size_t)c];
-                return !(v == "." || v == "?");
-            };
-            while (i < n) {
-                const std::string_view s = lines[i];
-                if (s.empty() || s[0] == '#' || s[0] == '_' || s == "loop_") break;
-                cif_tokens(s, tok);
-                ++i;
-                if ((int)tok.size() < ncol) continue;
+            ++ncol;
+            have = cif_next(p, begin, end, t, bare);
+        }
+        if (!site || ncol == 0) continue;   // some other loop: its values are skipped by the scan above
+        auto idx = [&](const char *key) { auto it = col.find(key); return it == col.end() ? -1 : it->second; };
+        const int c_model = idx("pdbx_PDB_model_num"), c_group = idx("group_PDB"), c_atom = idx("label_atom_id"),
+                  c_comp = idx("label_comp_id"), c_aseq = idx("auth_seq_id"), c_lseq = idx("label_seq_id"),
+                  c_achain = idx("auth_asym_id"), c_lchain = idx("label_asym_id"), c_x = idx("Cartn_x"), c_y = idx("Cartn_y"),
+                  c_z = idx("Cartn_z"), c_occ = idx("occupancy"), c_b = idx("B_iso_or_equiv"), c_id = idx("id"),
+                  c_charge = idx("pdbx_formal_charge"), c_sym = idx("type_symbol"), c_icode = idx("pdbx_PDB_ins_code"),
+                  c_alt = idx("label_alt_id");
+        // value of a column; false when the column is absent or holds "." / "?"
+        auto get = [&](int c, std::string_view &v) {
+            if (c < 0) return false;
+            v = tok[(size_t)c];
+            return !(v == "." || v == "?");
+        };
+        tok.clear();
+        while (have && !(bare && cif_ends_loop(t))) {
+            tok.push_back(t);
+            have = cif_next(p, begin, end, t, bare);
+            if ((int)tok.size() < ncol) continue;
+            {
                 std::string_view v;
                 const long model_no = get(c_model, v) ? parse_long(v) : 1;
                 auto mi = model_index.find(model_no);
@@ -522,9 +573,11 @@ PDB read_mmcif(const std::string &path) {
                 add_atom(model, has_chain ? chain : std::string_view(), has_seq ? parse_long(seq) : 0, icode, resname, alt, std::move(a),
                          &cur);
             }
-            continue;
+            tok.clear();
         }
-        ++i;
+        if (!tok.empty())
+            throw std::runtime_error("mmCIF _atom_site loop ends inside a row (" + std::to_string(tok.size()) + " of " +
+                                     std::to_string(ncol) + " values) in " + path);
     }
     reshuffle_conformers(pdb);
     return pdb;

@@ -37,6 +37,10 @@ thread_local std::string g_create_error;
 struct Points {
     float *d = nullptr;    // 3*n floats: x[n] y[n] z[n]
     uint4 *cap = nullptr;  // cap table (sasa_cap.cuh), n <= 128 only
+    // 128 < n <= 1024: the points as float4 and the chunked cap table (inner / ring masks in separate arrays)
+    float4 *d4 = nullptr;
+    uint4 *capm_in = nullptr, *capm_rg = nullptr;
+    CapDims capd = {};
 };
 
 struct SmallCfg {
@@ -119,7 +123,7 @@ void sphere_points_host(uint32_t n, float *x, float *y, float *z) {
     }
 }
 
-int get_points(sasa_b200_ctx *ctx, uint32_t n, const float **px, const uint4 **cap) {
+int get_points(sasa_b200_ctx *ctx, uint32_t n, const Points **out) {
     auto it = ctx->points.find(n);
     if (it == ctx->points.end()) {
         std::vector<float> h(3 * (size_t)n);
@@ -132,11 +136,32 @@ int get_points(sasa_b200_ctx *ctx, uint32_t n, const float **px, const uint4 **c
             cap_build_table(n, h.data(), h.data() + n, h.data() + 2 * (size_t)n, t.data());
             CU_TRY(ctx, cudaMalloc(&P.cap, t.size() * sizeof(uint32_t)));
             CU_TRY(ctx, cudaMemcpy(P.cap, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        } else if (n <= 1024) {   // chunked table for the large-structure path (sasa_cap.cuh, capm_atom)
+            static const int grid_n = [] {
+                const char *e = getenv("SASA_B200_CAPM_N");   // tuning aid: direction bins per axis (even)
+                const int v = e ? atoi(e) : 64;
+                return v >= 8 && v <= 256 && v % 2 == 0 ? v : 64;
+            }();
+            P.capd = cap_dims(grid_n, kCapL, (int)((n + 127) / 128));
+            const size_t words = cap_multi_words(P.capd);
+            std::vector<uint32_t> tin(words), trg(words);
+            cap_build_table_multi(n, h.data(), h.data() + n, h.data() + 2 * (size_t)n, P.capd, tin.data(), trg.data());
+            std::vector<float> h4(4 * (size_t)n, 0.0f);
+            for (uint32_t i = 0; i < n; ++i) {
+                h4[4 * (size_t)i + 0] = h[i];
+                h4[4 * (size_t)i + 1] = h[n + i];
+                h4[4 * (size_t)i + 2] = h[2 * (size_t)n + i];
+            }
+            CU_TRY(ctx, cudaMalloc(&P.d4, h4.size() * sizeof(float)));
+            CU_TRY(ctx, cudaMemcpy(P.d4, h4.data(), h4.size() * sizeof(float), cudaMemcpyHostToDevice));
+            CU_TRY(ctx, cudaMalloc(&P.capm_in, words * sizeof(uint32_t)));
+            CU_TRY(ctx, cudaMalloc(&P.capm_rg, words * sizeof(uint32_t)));
+            CU_TRY(ctx, cudaMemcpy(P.capm_in, tin.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            CU_TRY(ctx, cudaMemcpy(P.capm_rg, trg.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
         it = ctx->points.emplace(n, P).first;
     }
-    *px = it->second.d;
-    *cap = it->second.cap;
+    *out = &it->second;
     return SASA_B200_OK;
 }
 
@@ -337,8 +362,7 @@ struct RunArgs {
     const uint32_t *d_cls;
     sasa_b200_outputs d_out;
     sasa_b200_params prm;
-    const float *d_points;
-    const uint4 *d_cap;
+    const Points *pts;
 };
 
 int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
@@ -355,10 +379,14 @@ int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
     kp->out_seg = b->n_seg ? ra.d_out.seg_sasa : nullptr;
     kp->out_protein = ra.d_out.protein;
     const uint32_t n = ra.prm.n_points;
-    kp->cap = ra.d_cap;
-    kp->px = ra.d_points;
-    kp->py = ra.d_points + n;
-    kp->pz = ra.d_points + 2 * (size_t)n;
+    kp->cap = ra.pts->cap;
+    kp->capm_in = ra.pts->capm_in;
+    kp->capm_rg = ra.pts->capm_rg;
+    kp->pts4 = ra.pts->d4;
+    kp->capd = ra.pts->capd;
+    kp->px = ra.pts->d;
+    kp->py = ra.pts->d + n;
+    kp->pz = ra.pts->d + 2 * (size_t)n;
     kp->n_points = n;
     const uint32_t lanes = ra.prm.simd_lanes ? ra.prm.simd_lanes : 8;
     kp->n_body = (n / lanes) * lanes;
@@ -418,7 +446,7 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
         if (L.cfg < 0) {
             if (ctx->large_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_large, 0));
             int rc = large_enqueue(ctx->sm_count, ctx->large, kp, &b->h_order[variant][L.order_off], L.n_work,
-                                   b->h_off.data(), st, launches);
+                                   b->h_off.data(), b->h_seg_off.empty() ? nullptr : b->h_seg_off.data(), st, launches);
             if (rc != 0) return fail(ctx, rc, "large-structure path failed: %s", cudaGetErrorString(cudaGetLastError()));
             CU_TRY(ctx, cudaEventRecord(ctx->ev_large, st));
             ctx->large_used = true;
@@ -550,7 +578,9 @@ void sasa_b200_destroy(sasa_b200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (auto &kv : ctx->points) { cudaFree(kv.second.d); cudaFree(kv.second.cap); }
+    for (auto &kv : ctx->points) {
+        cudaFree(kv.second.d); cudaFree(kv.second.cap); cudaFree(kv.second.d4); cudaFree(kv.second.capm_in); cudaFree(kv.second.capm_rg);
+    }
     for (int i = 0; i < kStreams; ++i)
         if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
     for (int i = 0; i < sasa_b200_ctx::kSide; ++i) {
@@ -706,7 +736,7 @@ int sasa_b200_batch_run_device(sasa_b200_batch *b, const float *d_xyzr, const ui
     ra.d_cls = d_id_class;
     ra.d_out = *d_out;
     ra.prm = *params;
-    if ((rc = get_points(ctx, params->n_points, &ra.d_points, &ra.d_cap)) != 0) return rc;
+    if ((rc = get_points(ctx, params->n_points, &ra.pts)) != 0) return rc;
     const int variant = (d_id_class ? 1 : 0) + 2;
     KParams base;
     make_kparams(b, ra, &base);
@@ -772,7 +802,7 @@ static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz
     ra.d_out.seg_sasa = (out->seg_sasa && G) ? reinterpret_cast<float *>(base_p + o_seg) : nullptr;
     ra.d_out.protein = out->protein ? reinterpret_cast<float *>(base_p + o_prot) : nullptr;
     ra.prm = *params;
-    if ((rc = get_points(ctx, params->n_points, &ra.d_points, &ra.d_cap)) != 0) return rc;
+    if ((rc = get_points(ctx, params->n_points, &ra.pts)) != 0) return rc;
     KParams kbase;
     make_kparams(b, ra, &kbase);
     b->launches_last = 0;
@@ -873,7 +903,7 @@ static int run_atom_range_locked(sasa_b200_batch *b, const float *d_xyzr, const 
     ra.d_cls = d_cls;
     ra.d_out = sasa_b200_outputs{d_counts, d_atom, nullptr, nullptr};
     ra.prm = *params;
-    if ((rc = get_points(ctx, params->n_points, &ra.d_points, &ra.d_cap)) != 0) return rc;
+    if ((rc = get_points(ctx, params->n_points, &ra.pts)) != 0) return rc;
     KParams kp;
     make_kparams(b, ra, &kp);
     kp.seg_be = nullptr;
@@ -884,7 +914,8 @@ static int run_atom_range_locked(sasa_b200_batch *b, const float *d_xyzr, const 
     std::vector<uint32_t> order(b->S);
     std::iota(order.begin(), order.end(), 0u);
     if (ctx->large_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_large, 0));
-    rc = large_enqueue(ctx->sm_count, ctx->large, kp, order.data(), (uint32_t)b->S, b->h_off.data(), st, &b->launches_last, rank, n_ranks);
+    rc = large_enqueue(ctx->sm_count, ctx->large, kp, order.data(), (uint32_t)b->S, b->h_off.data(), nullptr, st, &b->launches_last, rank,
+                       n_ranks);
     if (rc == 0) {
         CU_TRY(ctx, cudaEventRecord(ctx->ev_large, st));
         ctx->large_used = true;
@@ -957,10 +988,9 @@ int sasa_b200_batch_reduce_device(sasa_b200_batch *b, const float *d_atom_sasa, 
     for (size_t s = 0; s < b->S; ++s) {
         const uint32_t a0 = b->h_off[s];
         const int N = (int)(b->h_off[s + 1] - a0);
-        const uint32_t nseg = b->h_seg_off.empty() ? 0 : b->h_seg_off[s + 1] - b->h_seg_off[s];
-        const int grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->sm_count, (nseg + 255) / 256 + 1));
-        large_sums_kernel<<<grid, 256, 0, st>>>(kp, (uint32_t)s, N, d_atom_sasa + a0, nullptr);
-        ++b->launches_last;
+        const uint32_t g0 = b->h_seg_off.empty() ? 0 : b->h_seg_off[s];
+        const uint32_t nseg = b->h_seg_off.empty() ? 0 : b->h_seg_off[s + 1] - g0;
+        large_enqueue_sums(ctx->sm_count, kp, (uint32_t)s, N, g0, nseg, d_atom_sasa + a0, nullptr, nullptr, 0, st, &b->launches_last);
     }
     CU_TRY(ctx, cudaGetLastError());
     return SASA_B200_OK;

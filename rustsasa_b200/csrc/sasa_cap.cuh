@@ -120,6 +120,78 @@ inline void cap_build_table(uint32_t n, const float *px, const float *py, const 
     for (auto &th : pool) th.join();
 }
 
+// ---- host: chunked tables for 128 < n <= 1024 points -------------------------------------------------------------------
+// The point set is cut into chunks of 128 consecutive points (the golden spiral orders points by latitude, so a chunk is
+// a latitude band); bin b holds, for every chunk c < nchp (the power of two >= the number of chunks), one 128-bit inner
+// mask at inner[b * nchp + c] and one ring mask at ring[b * nchp + c].  Inner and ring live in separate arrays because the
+// kernel's first pass reads inner masks only.  Same bins, margins and semantics as cap_build_table; grid size N and level
+// count L are run-time values here (a 64 x 64 x 66 table of 8 chunks is 2 x 34.6 MB and stays in the 126 MB L2).
+inline CapDims cap_dims(int N, int L, int nchunks) {
+    CapDims D;
+    D.half = 0.5f * (float)N;
+    D.scale = 0.5f * (float)N * (1.0f - 1.0f / 65536.0f);
+    D.lhalf = 0.5f * (float)L;
+    D.n = N;
+    D.levels = L + 2;
+    D.nchp_shift = 0;
+    while ((1 << D.nchp_shift) < nchunks) ++D.nchp_shift;
+    D.bin_degenerate = (unsigned)((size_t)D.levels * N * N);
+    D.bin_empty = D.bin_degenerate + 1;
+    return D;
+}
+inline size_t cap_multi_words(const CapDims &D) { return ((size_t)D.levels * D.n * D.n + 2) * ((size_t)4 << D.nchp_shift); }
+
+inline void cap_build_table_multi(uint32_t n, const float *px, const float *py, const float *pz, const CapDims &D,
+                                  uint32_t *inner, uint32_t *ring /* cap_multi_words(D) each */) {
+    const int N = D.n, L = D.levels - 2, levels = D.levels;
+    const size_t stride = (size_t)4 << D.nchp_shift;   // u32 words per bin
+    memset(inner, 0, cap_multi_words(D) * sizeof(uint32_t));
+    memset(ring, 0, cap_multi_words(D) * sizeof(uint32_t));
+    for (uint32_t p = 0; p < n; ++p) ring[(size_t)D.bin_degenerate * stride + (p >> 5)] |= 1u << (p & 31);
+    std::vector<double> lo(levels), hi(levels);
+    for (int l = 0; l < levels; ++l) {
+        lo[l] = l == 0 ? -INFINITY : -1.0 + 2.0 * (l - 1) / L;
+        hi[l] = l == levels - 1 ? INFINITY : -1.0 + 2.0 * l / L;
+    }
+    auto rows = [&](int iv0, int iv1) {
+        for (int iv = iv0; iv < iv1; ++iv)
+            for (int iu = 0; iu < N; ++iu) {
+                const double u0 = -1.0 + 2.0 * iu / N, u1 = -1.0 + 2.0 * (iu + 1) / N;
+                const double v0 = -1.0 + 2.0 * iv / N, v1 = -1.0 + 2.0 * (iv + 1) / N;
+                double c[3], k[3];
+                cap_oct_dir(0.5 * (u0 + u1), 0.5 * (v0 + v1), c);
+                double rho = 0.0;
+                const double cu[4] = {u0, u1, u0, u1}, cv[4] = {v0, v0, v1, v1};
+                for (int t = 0; t < 4; ++t) {
+                    cap_oct_dir(cu[t], cv[t], k);
+                    rho = std::max(rho, std::acos(std::min(1.0, std::max(-1.0, c[0] * k[0] + c[1] * k[1] + c[2] * k[2]))));
+                }
+                rho += kCapEpsAng;
+                for (uint32_t p = 0; p < n; ++p) {
+                    const double x = px[p], y = py[p], z = pz[p], len = std::sqrt(x * x + y * y + z * z);
+                    const double alpha = std::acos(std::min(1.0, std::max(-1.0, (c[0] * x + c[1] * y + c[2] * z) / len)));
+                    const double dmax = len * std::cos(std::max(alpha - rho, 0.0)), dmin = len * std::cos(std::min(alpha + rho, M_PI));
+                    const uint32_t bit = 1u << (p & 31);
+                    const size_t word = p >> 5;   // chunk (p >> 7) * 4 + word within the chunk: consecutive
+                    // levels are ordered: inner for l > l_in, ring for l_out <= l <= l_in, nothing below
+                    for (int l = 0; l < levels; ++l) {
+                        const bool in = dmax < lo[l] - kCapEpsC;
+                        const bool out = dmin < hi[l] + kCapEpsC;
+                        if (!in && !out) continue;
+                        const size_t e = (((size_t)l * N + iv) * N + iu) * stride + word;
+                        if (in) inner[e] |= bit;
+                        else ring[e] |= bit;
+                    }
+                }
+            }
+    };
+    const int nt = std::max(1, std::min<int>((int)std::thread::hardware_concurrency(), 16));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(rows, N * t / nt, N * (t + 1) / nt);
+    rows(0, N / nt);
+    for (auto &th : pool) th.join();
+}
+
 // ---- device ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float cap_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float cap_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -281,6 +353,116 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const Ato
     }
 #endif
     return n_points - cap_covered(a0, a1, a2, a3);
+}
+
+// ---- chunked cap tables: 128 < n_points <= 1024 --------------------------------------------------------------------------
+// Bin of entry e with run-time grid dimensions (same arithmetic as cap_bin).
+__device__ __forceinline__ unsigned cap_bin_rt(const float4 e, float vmag, const CapDims &D) {
+    const float c = e.w * cap_rsqrt(vmag);
+    const float s = cap_rcp(fabsf(e.x) + fabsf(e.y) + fabsf(e.z));
+    float u = e.x * s, v = e.y * s;
+    if (e.z < 0.0f) {
+        const float uu = copysignf(1.0f - fabsf(v), u);
+        v = copysignf(1.0f - fabsf(u), v);
+        u = uu;
+    }
+    const int iu = __float2int_rd(fmaf(u, D.scale, D.half));
+    const int iv = __float2int_rd(fmaf(v, D.scale, D.half));
+    const int l = min(max(__float2int_rd(fmaf(c, D.lhalf, D.lhalf + 1.0f)), 0), D.levels - 1);
+    return (unsigned)((l * D.n + iv) * D.n + iu);
+}
+
+// One atom against the chunked table.  NCHP (2, 4 or 8) lanes share a neighbour, one lane per 128-point chunk: lane l
+// owns chunk l mod NCHP of neighbour (l div NCHP) of every round of 32 / NCHP neighbours, so the 128-bit coverage of a
+// chunk stays in four registers of the lanes that own it and a neighbour's NCHP masks are one contiguous read.
+//   bins     lane q of a round of 32: entry (reference arithmetic) -> bin, packed with the candidate index into nbp[q]
+//   pass 1   OR of the inner masks over all neighbours; a buried atom (every point inside some inner cap -- the common
+//            case: 94 % of all points are) ends here with no point test at all
+//   pass 2   per (neighbour, chunk): ring points not yet covered take the reference's exact test; hits join the coverage
+// Returns the exposed-point count.  nb: candidate indices (into `atoms`) of the k <= 128 neighbours; nbp: 128 u32 of scratch.
+template <int NCHP, class Atoms, class IdxT>
+__device__ __forceinline__ int capm_atom(const uint4 *__restrict__ tin, const uint4 *__restrict__ trg, const CapDims &D,
+                                         const Atoms &atoms, const float4 ai, float probe, const IdxT *nb, int k, uint32_t *nbp,
+                                         const float4 *__restrict__ pts4, int n_points, int nbody) {
+    static_assert(NCHP == 2 || NCHP == 4 || NCHP == 8, "chunk lanes");
+    constexpr int PER = 32 / NCHP;
+    const int lane = lane_id();
+    const int ch = lane & (NCHP - 1), sub = lane / NCHP;
+    const float r = __fadd_rn(ai.w, probe);
+    const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
+#pragma unroll 1
+    for (int q0 = 0; q0 < k; q0 += 32) {
+        const int q = q0 + lane;
+        if (q < k) {
+            const unsigned j = (unsigned)nb[q];
+            float vmag;
+            const float4 e = make_entry(ai, atoms((int)j), probe, r2, two_r, &vmag);
+            const unsigned bin = vmag >= kCapMinV2 ? cap_bin_rt(e, vmag, D) : D.bin_degenerate;
+            nbp[q] = (bin << 9) | j;
+        }
+    }
+    __syncwarp();
+    // points of this lane's chunk that exist: [128 ch, 128 ch + 128) intersected with [0, n_points)
+    unsigned vm[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const int left = n_points - (128 * ch + 32 * w);
+        vm[w] = left >= 32 ? 0xffffffffu : (left > 0 ? (0xffffffffu >> (32 - left)) : 0u);
+    }
+    unsigned a[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 2
+    for (int q0 = 0; q0 < k; q0 += PER) {
+        const int q = q0 + sub;
+        if (q < k) {
+            const uint4 m = __ldg(tin + (((size_t)(nbp[q] >> 9)) << D.nchp_shift) + ch);
+            a[0] |= m.x; a[1] |= m.y; a[2] |= m.z; a[3] |= m.w;
+        }
+    }
+#pragma unroll
+    for (int d = NCHP; d < 32; d <<= 1)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) a[w] |= __shfl_xor_sync(kFull, a[w], d);
+    const bool open = ((vm[0] & ~a[0]) | (vm[1] & ~a[1]) | (vm[2] & ~a[2]) | (vm[3] & ~a[3])) != 0u;
+    if (!__any_sync(kFull, open)) return 0;
+    // pass 2: exact tests of the uncovered ring points
+#pragma unroll 1
+    for (int q0 = 0; q0 < k; q0 += PER) {
+        const int q = q0 + sub;
+        unsigned m[4] = {0u, 0u, 0u, 0u};
+        unsigned j = 0;
+        if (q < k && open) {
+            const unsigned pk = nbp[q];
+            j = pk & 511u;
+            const uint4 g = __ldg(trg + (((size_t)(pk >> 9)) << D.nchp_shift) + ch);
+            m[0] = g.x & vm[0] & ~a[0]; m[1] = g.y & vm[1] & ~a[1]; m[2] = g.z & vm[2] & ~a[2]; m[3] = g.w & vm[3] & ~a[3];
+        }
+        if (!__any_sync(kFull, (m[0] | m[1] | m[2] | m[3]) != 0u)) continue;
+        if ((m[0] | m[1] | m[2] | m[3]) != 0u) {
+            float vmag;
+            const float4 e = make_entry(ai, atoms((int)j), probe, r2, two_r, &vmag);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                unsigned mw = m[w];
+                while (mw) {
+                    const int b = 31 - __clz(mw);
+                    const unsigned bit = 1u << b;
+                    mw ^= bit;
+                    const int pt = 128 * ch + 32 * w + b;
+                    const float4 P = __ldg(pts4 + pt);
+                    const bool hit = pt >= nbody ? dot_tail(P.x, P.y, P.z, e) <= e.w : dot_body(P.x, P.y, P.z, e) < e.w;
+                    if (hit) a[w] |= bit;
+                }
+            }
+        }
+    }
+    // hits found by the other lanes of the same chunk
+#pragma unroll
+    for (int d = NCHP; d < 32; d <<= 1)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) a[w] |= __shfl_xor_sync(kFull, a[w], d);
+    int exposed = 0;
+    if (sub == 0) exposed = __popc(vm[0] & ~a[0]) + __popc(vm[1] & ~a[1]) + __popc(vm[2] & ~a[2]) + __popc(vm[3] & ~a[3]);
+    return __reduce_add_sync(kFull, exposed);
 }
 
 }  // namespace sasa

@@ -25,6 +25,14 @@ constexpr float kCutSlack = 1.0e-3f;  // Angstrom; keeps exactly-tangent pairs i
 constexpr float kCellSafety = 1.0002f;
 constexpr double kBoundaryTol = 1.0e-5;
 
+// Dimensions of a chunked cap table (sasa_cap.cuh, 128 < n_points <= 1024).
+struct CapDims {
+    float half, scale;      // direction: iu = floor(u * scale + half)
+    float lhalf;            // level:     l  = clamp(floor(c * lhalf + lhalf + 1), 0, levels - 1)
+    int n, levels, nchp_shift;
+    unsigned bin_degenerate, bin_empty;
+};
+
 struct KParams {
     // batch (device pointers)
     const float4 *xyzr;
@@ -45,6 +53,9 @@ struct KParams {
     // sphere points (SoA) and run parameters
     const float *px, *py, *pz;
     const uint4 *cap;             // cap table of this point set (sasa_cap.cuh), n_points <= 128 only; else null
+    const uint4 *capm_in, *capm_rg;   // chunked cap table (inner / ring masks), 128 < n_points <= 1024; else null
+    const float4 *pts4;           // the points as float4 (chunked cap path)
+    CapDims capd;
     uint32_t n_points, n_body;
     float inv_n, probe;
     float near2;                  // squared centre distance below which a neighbour is "near"

@@ -275,12 +275,40 @@ __device__ __forceinline__ bool structure_setup(const KParams &p, const SmemView
     return true;
 }
 
+// Sequential f32 sum of v[0, n) in index order (simd_sum, src/utils.rs:14-22) by ONE thread, starting from `t`.  The
+// additions form a dependent chain (4 cycles each) that no reordering may shorten, but the loads need not sit on it:
+// sixteen values are fetched ahead of every sixteen additions (a plain `t += v[i]` loop costs a shared-memory round
+// trip per element: 190 us per 5,000-atom structure, the barrier stall of profiles/r02a_cfg3_tight.txt).
+__device__ __forceinline__ float seq_sum(const float *v, int n, float t) {
+    int i = 0;
+    // v is 16-byte aligned (SmallLayout: the atom region in front of it is a multiple of 16 bytes)
+    const float4 *v4 = reinterpret_cast<const float4 *>(v);
+    for (; i + 16 <= n; i += 16) {
+        const float4 a = v4[(i >> 2) + 0], b = v4[(i >> 2) + 1], c = v4[(i >> 2) + 2], d = v4[(i >> 2) + 3];
+        t = __fadd_rn(t, a.x); t = __fadd_rn(t, a.y); t = __fadd_rn(t, a.z); t = __fadd_rn(t, a.w);
+        t = __fadd_rn(t, b.x); t = __fadd_rn(t, b.y); t = __fadd_rn(t, b.z); t = __fadd_rn(t, b.w);
+        t = __fadd_rn(t, c.x); t = __fadd_rn(t, c.y); t = __fadd_rn(t, c.z); t = __fadd_rn(t, c.w);
+        t = __fadd_rn(t, d.x); t = __fadd_rn(t, d.y); t = __fadd_rn(t, d.z); t = __fadd_rn(t, d.w);
+    }
+    for (; i < n; ++i) t = __fadd_rn(t, v[i]);
+    return t;
+}
+
 // Per-atom counts -> areas (coalesced stores), then the level sums in the reference's order: replaces the
 // numeric part of process_atoms (src/options.rs:195-232, :292-315, :370-410) and simd_sum (src/utils.rs:14-22).
 // AREA_READY: val already holds areas and the counts have been written (tight kernel).
+// Every sum keeps the reference's order (bit-identical results) but only the two chains that ARE sequential run on a
+// single thread: residue / chain sums are one thread each; the ProteinLevel polar / non-polar totals -- running sums of
+// the residue sums in residue order (src/options.rs:376-403) -- take the residue sums from a shared-memory scratch
+// (`scratch`: the per-warp blocks, idle between structures) instead of recomputing them with dependent loads; the global
+// total (src/options.rs:404) is seq_sum over all atoms.  The two chains run concurrently on threads 0 and 32.
 template <int NT, bool AREA_READY = false>
-__device__ __forceinline__ void structure_outputs(const KParams &p, const SmemView &V, uint32_t sid, uint32_t a0, int N) {
+__device__ __forceinline__ void structure_outputs(const KParams &p, const SmemView &V, uint32_t sid, uint32_t a0, int N,
+                                                  unsigned char *scratch) {
     const int tid = threadIdx.x;
+    constexpr int kScratch = (int)(((size_t)(NT / 32) * kWarpBlockBytes / 5) & ~(size_t)3);   // 4 B sum + 1 B polar flag each
+    float *const s_sum = reinterpret_cast<float *>(scratch);
+    uint8_t *const s_pol = scratch + (size_t)kScratch * 4;
     if (AREA_READY) {
         if (p.out_atom)
             for (int i = tid; i < N; i += NT) p.out_atom[a0 + i] = V.val[i];
@@ -296,8 +324,46 @@ __device__ __forceinline__ void structure_outputs(const KParams &p, const SmemVi
     }
     if (p.seg_be) {
         const uint32_t g0 = p.struct_seg_off[sid], g1 = p.struct_seg_off[sid + 1];
-        if (p.out_seg) {
-            // sequential f32 sum in atom order, one thread per segment
+        if (p.out_protein) {
+            float polar = 0.0f, nonpolar = 0.0f;
+            for (uint32_t base = g0; base < g1; base += (uint32_t)kScratch) {
+                const uint32_t gend = min(g1, base + (uint32_t)kScratch);
+                // sequential f32 sum in atom order, one thread per segment
+                for (uint32_t k = base + tid; k < gend; k += NT) {
+                    const uint2 be = p.seg_be[k];
+                    float t = 0.0f;
+                    for (uint32_t i = be.x; i < be.y && i < (uint32_t)N; ++i) t = __fadd_rn(t, V.val[i]);
+                    if (p.out_seg) p.out_seg[k] = t;
+                    s_sum[k - base] = t;
+                    s_pol[k - base] = p.seg_polar ? p.seg_polar[k] : (uint8_t)0;
+                }
+                __syncthreads();
+                if (tid == 32 % NT) {
+                    const int n = (int)(gend - base);
+                    int k = 0;
+                    for (; k + 8 <= n; k += 8) {   // loads ahead of the dependent additions
+                        float t[8];
+                        uint8_t f[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { t[u] = s_sum[k + u]; f[u] = s_pol[k + u]; }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (f[u]) polar = __fadd_rn(polar, t[u]);
+                            else nonpolar = __fadd_rn(nonpolar, t[u]);
+                        }
+                    }
+                    for (; k < n; ++k) {
+                        if (s_pol[k]) polar = __fadd_rn(polar, s_sum[k]);
+                        else nonpolar = __fadd_rn(nonpolar, s_sum[k]);
+                    }
+                }
+                if (gend < g1) __syncthreads();   // the scratch is refilled by the next round
+            }
+            if (tid == 32 % NT) {
+                p.out_protein[3 * (size_t)sid + 1] = polar;
+                p.out_protein[3 * (size_t)sid + 2] = nonpolar;
+            }
+        } else if (p.out_seg) {
             for (uint32_t k = g0 + tid; k < g1; k += NT) {
                 const uint2 be = p.seg_be[k];
                 float t = 0.0f;
@@ -305,23 +371,9 @@ __device__ __forceinline__ void structure_outputs(const KParams &p, const SmemVi
                 p.out_seg[k] = t;
             }
         }
-        if (p.out_protein && tid == 32 % NT) {
-            // polar / non-polar: running sums of residue sums in residue order (src/options.rs:376-403)
-            float polar = 0.0f, nonpolar = 0.0f;
-            for (uint32_t k = g0; k < g1; ++k) {
-                const uint2 be = p.seg_be[k];
-                float t = 0.0f;
-                for (uint32_t i = be.x; i < be.y && i < (uint32_t)N; ++i) t = __fadd_rn(t, V.val[i]);
-                if (p.seg_polar && p.seg_polar[k]) polar = __fadd_rn(polar, t);
-                else nonpolar = __fadd_rn(nonpolar, t);
-            }
-            p.out_protein[3 * (size_t)sid + 1] = polar;
-            p.out_protein[3 * (size_t)sid + 2] = nonpolar;
-        }
     }
     if (p.out_protein && tid == 0) {
-        float t = 0.0f;   // global_total = simd_sum(atom_sasa), src/options.rs:404
-        for (int i = 0; i < N; ++i) t = __fadd_rn(t, V.val[i]);
+        const float t = seq_sum(V.val, N, 0.0f);   // global_total = simd_sum(atom_sasa), src/options.rs:404
         p.out_protein[3 * (size_t)sid + 0] = t;
         if (!p.seg_be) { p.out_protein[3 * (size_t)sid + 1] = 0.0f; p.out_protein[3 * (size_t)sid + 2] = t; }
     }
@@ -446,7 +498,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
             if (streamed) atomicAdd(p.stat + 2, (unsigned long long)streamed);
         }
         __syncthreads();
-        structure_outputs<NT>(p, V, sid, a0, N);
+        structure_outputs<NT>(p, V, sid, a0, N, smem + kOffWarpBlocks);
     }
 }
 

@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
             if (V.misc[6]) atomicAdd(p.stat + 1, (unsigned long long)(unsigned)V.misc[6]);
             if (V.misc[7]) atomicAdd(p.stat + 2, (unsigned long long)(unsigned)V.misc[7]);
         }
-        structure_outputs<NT, SASA_OPT_AREA != 0>(p, V, sid, a0, N);
+        structure_outputs<NT, SASA_OPT_AREA != 0>(p, V, sid, a0, N, smem + kOffWarpBlocks);
     }
 }
 

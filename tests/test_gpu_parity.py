@@ -476,3 +476,65 @@ def test_cap_table_randomised_geometry(eng, oracle, seed):
         assert np.array_equal(r.counts[a0:a1], o["counts"]), (seed, i, n_points, lanes, probe)
         assert np.array_equal(r.atom_sasa[a0:a1], o["sasa"]), (seed, i)
     b.close()
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_chunked_cap_table_randomised_geometry(eng, seed):
+    """The chunked cap table of the large-structure path (capm_atom, 128 < n_points <= 1024): random point counts around the
+    chunk boundaries, lane rules, probe radii, radii from 0.4 to 3.2 A, coincident centres, a dense cluster (more than 128
+    neighbours: cold path) and a cell block with more than 288 candidates (staging overflow), one structure with id
+    classes (generic kernel).  Counts and areas must equal the oracle's exactly."""
+    from oracle import load
+    fast = load(fast=True)
+    rng = np.random.default_rng(7700 + seed)
+    n_points = int([129, 200, 256, 257, 500, 513, 960, 1000, 1023, 1024][int(rng.integers(0, 10))])
+    lanes = int(rng.choice([4, 8, 16]))
+    probe = float(rng.choice([0.0, 0.8, 1.4, 2.2]))
+    structs = []
+    for t in range(3):
+        n = int(rng.integers(6000, 14000))
+        density = float(rng.choice([0.02, 0.057, 0.09]))
+        side = (n / density) ** (1.0 / 3.0)
+        xyz = rng.uniform(0.0, side, size=(n, 3)) + rng.uniform(-200, 200, size=3)
+        rad = rng.uniform(0.4, 3.2, size=n) if t == 1 else rng.choice([1.42, 1.61, 1.76, 1.88], size=n)
+        xyz[1] = xyz[0]
+        xyz[3] = xyz[2] + 1e-4
+        rad[7], xyz[7] = 3.2, xyz[6] + 0.2
+        if t == 2:   # 300 atoms inside a 5 A ball: > 128 neighbours each and > 288 candidates in the cell block
+            xyz[100:400] = xyz[50] + rng.normal(scale=1.6, size=(300, 3))
+        structs.append(np.concatenate([xyz, rad[:, None]], axis=1).astype(np.float32))
+    off = np.cumsum([0] + [s.shape[0] for s in structs]).astype(np.uint64)
+    xyzr = np.concatenate(structs)
+    b = eng.batch(off)
+    r = b.run_host(xyzr, probe_radius=probe, n_points=n_points, simd_lanes=lanes, want=("counts", "atom"))
+    want = [fast.calculate_sasa_internal(s, probe, n_points, lanes=lanes, threads=-1) for s in structs]
+    for i, o in enumerate(want):
+        a0, a1 = int(off[i]), int(off[i + 1])
+        assert np.array_equal(r.counts[a0:a1], o["counts"]), (seed, i, n_points, lanes, probe)
+        assert np.array_equal(r.atom_sasa[a0:a1], o["sasa"]), (seed, i)
+    assert r.stats["streamed_atoms"] > 0
+    # the same atoms with id classes (every atom its own class except two pairs): generic kernel, same answers
+    cls = np.arange(xyzr.shape[0], dtype=np.uint32)
+    r2 = b.run_host(xyzr, id_class=cls, probe_radius=probe, n_points=n_points, simd_lanes=lanes, want=("counts",))
+    assert np.array_equal(r2.counts, r.counts)
+    b.close()
+
+
+def test_large_path_non_finite_and_empty(eng):
+    """A non-finite coordinate in a structure of the large path: status 4, outputs blanked, context usable; an atom-range
+    batch with an empty structure."""
+    from rustsasa_b200 import SasaB200Error
+    from rustsasa_b200 import workloads as W
+    a = W.large_assembly(8000)
+    bad = a.xyzr.copy()
+    bad[4321, 2] = np.inf
+    with pytest.raises(SasaB200Error) as ei:
+        eng.calculate_sasa_internal(bad)
+    assert ei.value.code == 4
+    good = eng.calculate_sasa_internal(a.xyzr)
+    assert np.isfinite(good).all() and good.shape[0] == a.n_atoms
+    n = a.n_atoms
+    b = eng.batch([0, 0, n, n])
+    parts = [b.run_atom_range_host(a.xyzr, r, 2) for r in range(2)]
+    assert np.array_equal(parts[0].atom_sasa + parts[1].atom_sasa, good)
+    b.close()
