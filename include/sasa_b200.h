@@ -66,8 +66,9 @@ typedef enum sasa_b200_status {
     SASA_B200_ERR_UNSUPPORTED = 5
 } sasa_b200_status;
 
-typedef struct sasa_b200_ctx sasa_b200_ctx;     /* one per (process, device); thread-compatible */
+typedef struct sasa_b200_ctx sasa_b200_ctx;     /* one per (process, device); shareable between threads */
 typedef struct sasa_b200_batch sasa_b200_batch; /* topology of a batch: reusable across runs   */
+typedef struct sasa_b200_job sasa_b200_job;     /* one host-buffer run in flight (submit .. wait) */
 
 /* Numeric parameters of one run: the arguments of calculate_sasa_internal
  * (src/lib.rs:249-254) plus the lane count of the mirrored reference build. */
@@ -121,7 +122,8 @@ SASA_B200_API int sasa_b200_free_pinned(void *ptr);
 SASA_B200_API int sasa_b200_sphere_points(uint32_t n_points, float *xyz);
 
 /* ---- replaces calculate_sasa_internal (src/lib.rs:249-298) -------------------------
- * One structure, host buffers, synchronous.  xyzr = n_atoms * 4 floats.  ids may be NULL
+ * One structure, host buffers, synchronous.  Safe to call from many threads at once on one context (the reference's
+ * directory mode does, src/main.rs:375, :439): each call runs on a stream and workspace of its own.  xyzr = n_atoms * 4 floats.  ids may be NULL
  * (all distinct) or n_atoms 64-bit Atom.id values.  out_sasa receives n_atoms floats;
  * out_counts (nullable) the integer exposed-point counts.  n_atoms == 0 is a no-op
  * (tests/sanity.rs:148-157). */
@@ -146,6 +148,18 @@ SASA_B200_API void sasa_b200_batch_destroy(sasa_b200_batch *batch);
 SASA_B200_API int sasa_b200_batch_run_host(sasa_b200_batch *batch, const float *xyzr, const uint32_t *id_class,
                              const sasa_b200_params *params, const sasa_b200_outputs *out,
                              sasa_b200_stats *stats /* nullable */);
+
+/* The same run as an asynchronous pair ("async submit/wait pair for stream overlap").  submit enqueues the
+ * copies and kernels and returns; the input and output buffers belong to the run until sasa_b200_job_wait returns (use
+ * page-locked buffers: copies from pageable memory make submit block).  wait blocks until every requested output is in host
+ * memory, reports deferred errors and releases the job handle.  Several jobs of DIFFERENT batches may be in flight on one
+ * context, from any threads; a batch itself carries one run at a time.  This is what lets a caller parse and pack tile
+ * k + 1 while tile k is on the GPU (directory mode, src/main.rs:342-480). */
+SASA_B200_API int sasa_b200_batch_submit_host(sasa_b200_batch *batch, const float *xyzr, const uint32_t *id_class,
+                                const sasa_b200_params *params, const sasa_b200_outputs *out, sasa_b200_job **out_job);
+SASA_B200_API int sasa_b200_batch_submit_frames_host(sasa_b200_batch *batch, const float *xyz, const float *radii,
+                                       const sasa_b200_params *params, const sasa_b200_outputs *out, sasa_b200_job **out_job);
+SASA_B200_API int sasa_b200_job_wait(sasa_b200_job *job, sasa_b200_stats *stats /* nullable */);
 
 /* Same computation with every data pointer (xyzr, id_class, outputs) already in DEVICE
  * memory; enqueues on `stream` (a cudaStream_t, NULL = the context's stream) and returns

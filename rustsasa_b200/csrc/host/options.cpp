@@ -238,6 +238,38 @@ std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &pa
     }
     const size_t N = struct_off[S], G = seg_off[S];
     sasa_b200_ctx *ctx = context();
+    if (S == 1 && N > 0) {
+        // One structure (SASAOptions::process, src/options.rs:606-618): the engine's one-structure call runs on a stream and
+        // workspace of its own, so callers on many threads overlap (the reference's directory mode, src/main.rs:375).
+        const Packed &p = *packed[0];
+        const std::vector<std::uint32_t> cls = id_classes(p.ids, 0);
+        std::vector<float> atom(level == LevelKind::Atom ? N : 0), seg(G);
+        float prot[3] = {0.0f, 0.0f, 0.0f};
+        sasa_b200_params prm{opt.probe_radius, (std::uint32_t)opt.n_points, 8, (std::int32_t)opt.threads, 0};
+        sasa_b200_outputs outs{nullptr, level == LevelKind::Atom ? atom.data() : nullptr,
+                               (level == LevelKind::Residue || level == LevelKind::Chain) && G ? seg.data() : nullptr,
+                               level == LevelKind::Protein ? prot : nullptr};
+        if (sasa_b200_run_batch(ctx, p.xyzr.data(), cls.empty() ? nullptr : cls.data(), struct_off.data(), 1, G ? p.seg_be.data() : nullptr,
+                                G ? seg_off.data() : nullptr, G ? p.seg_polar.data() : nullptr, &prm, &outs, nullptr) != SASA_B200_OK)
+            throw_device(ctx, "run_batch");
+        switch (level) {
+            case LevelKind::Atom: results.emplace_back(SASAResult(std::move(atom))); break;
+            case LevelKind::Residue: {
+                std::vector<ResidueResult> v = p.residue_meta;
+                for (size_t k = 0; k < v.size(); ++k) v[k].value = seg[k];
+                results.emplace_back(SASAResult(std::move(v)));
+                break;
+            }
+            case LevelKind::Chain: {
+                std::vector<ChainResult> v = p.chain_meta;
+                for (size_t k = 0; k < v.size(); ++k) v[k].value = seg[k];
+                results.emplace_back(SASAResult(std::move(v)));
+                break;
+            }
+            case LevelKind::Protein: results.emplace_back(SASAResult(ProteinResult{prot[0], prot[1], prot[2]})); break;
+        }
+        return results;
+    }
     // pinned staging: the pipelined host entry point overlaps H2D, kernels and D2H across chunks
     std::lock_guard<std::mutex> pin_lock(g_pin_mu);   // one tile at a time owns the staging buffer
     const size_t in_bytes = N * 16, out_atom = level == LevelKind::Atom ? N * 4 : 0, out_seg = G * 4, out_prot = S * 12;

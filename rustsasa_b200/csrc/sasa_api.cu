@@ -13,11 +13,13 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -54,9 +56,33 @@ struct SmallCfg {
 constexpr int kStreams = 3;
 constexpr size_t kChunkAtoms = 1000000;
 constexpr uint32_t kSingleLargeMin = 1024;   // atoms from which a lone structure takes the large-structure path
+constexpr size_t kMaxSlots = 16;
+
+// Everything one one-structure call needs, owned for the duration of the call.
+struct SingleSlot {
+    cudaStream_t st = nullptr;
+    LargeWorkspace large;
+    char *d_buf = nullptr;
+    size_t d_bytes = 0;
+    char *h_pin = nullptr;
+    size_t h_bytes = 0;
+    bool busy = false;
+};
 
 }  // namespace
 
+// One host-buffer run in flight (sasa_b200_batch_submit_host .. sasa_b200_job_wait).
+struct sasa_b200_job {
+    sasa_b200_batch *batch = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // timing: first enqueue .. everything done
+    void *d_arena = nullptr;                    // stream-ordered allocation holding inputs, outputs and the status words
+    unsigned long long *h_status = nullptr;     // pinned: [0] error flag, [1..3] statistics
+    std::chrono::steady_clock::time_point t_begin;
+    uint32_t launches = 0;
+    bool active = false;
+};
+
+struct sasa_b200_job;
 struct sasa_b200_ctx {
     int device = 0;
     int sm_count = 0;
@@ -83,6 +109,15 @@ struct sasa_b200_ctx {
     cudaEvent_t ev_large = nullptr;
     bool large_used = false;
     bool attr_done[8][6] = {};   // [kernel configuration][instantiation]: shared-memory attribute set (at first launch)
+    // jobs: one per host-buffer run in flight (submit / wait); recycled, so events and the pinned status word are made once
+    std::vector<sasa_b200_job *> free_jobs;
+    cudaEvent_t ev_tail[kStreams] = {};   // end of the previous job on each copy stream (the next job's first stream waits on them)
+    bool tail_valid = false;
+    // slots of the one-structure calls: own stream, own workspace, own staging -- callers on different threads do not
+    // serialise on the context (the reference's directory mode calls the engine from every rayon worker, src/main.rs:375)
+    std::vector<std::unique_ptr<SingleSlot>> slots;
+    std::mutex slot_mu;
+    std::condition_variable slot_cv;
 };
 
 namespace {
@@ -251,6 +286,7 @@ struct sasa_b200_batch {
     uint8_t *d_polar = nullptr;
     sasa_b200_stats last = {};
     uint32_t launches_last = 0;
+    sasa_b200_job *in_flight = nullptr;   // the work counters belong to one run at a time
 };
 
 namespace {
@@ -365,33 +401,22 @@ struct RunArgs {
     const Points *pts;
 };
 
-int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
-    sasa_b200_ctx *ctx = b->ctx;
-    memset(kp, 0, sizeof *kp);
-    kp->xyzr = ra.d_xyzr;
-    kp->cls = ra.d_cls;
-    kp->struct_off = b->d_off;
-    kp->seg_be = b->d_seg_be;
-    kp->struct_seg_off = b->d_seg_off;
-    kp->seg_polar = b->d_polar;
-    kp->out_counts = ra.d_out.counts;
-    kp->out_atom = ra.d_out.atom_sasa;
-    kp->out_seg = b->n_seg ? ra.d_out.seg_sasa : nullptr;
-    kp->out_protein = ra.d_out.protein;
-    const uint32_t n = ra.prm.n_points;
-    kp->cap = ra.pts->cap;
-    kp->capm_in = ra.pts->capm_in;
-    kp->capm_rg = ra.pts->capm_rg;
-    kp->pts4 = ra.pts->d4;
-    kp->capd = ra.pts->capd;
-    kp->px = ra.pts->d;
-    kp->py = ra.pts->d + n;
-    kp->pz = ra.pts->d + 2 * (size_t)n;
+// Sphere points, cap tables and numeric parameters of a run.
+void fill_run_params(KParams *kp, const Points *pts, const sasa_b200_params &prm) {
+    const uint32_t n = prm.n_points;
+    kp->cap = pts->cap;
+    kp->capm_in = pts->capm_in;
+    kp->capm_rg = pts->capm_rg;
+    kp->pts4 = pts->d4;
+    kp->capd = pts->capd;
+    kp->px = pts->d;
+    kp->py = pts->d + n;
+    kp->pz = pts->d + 2 * (size_t)n;
     kp->n_points = n;
-    const uint32_t lanes = ra.prm.simd_lanes ? ra.prm.simd_lanes : 8;
+    const uint32_t lanes = prm.simd_lanes ? prm.simd_lanes : 8;
     kp->n_body = (n / lanes) * lanes;
     kp->inv_n = 1.0f / (float)n;
-    kp->probe = ra.prm.probe_radius;
+    kp->probe = prm.probe_radius;
     static const float near_a = [] {
         const char *e = getenv("SASA_B200_NEAR");
         return e ? (float)atof(e) : 4.0f;
@@ -407,7 +432,23 @@ int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
     kp->m_min = m_min;
     kp->m_max = m_max;
     static const uint32_t nocache = getenv("SASA_B200_NOCACHE") ? 4u : 0u;   // tuning aid
-    kp->flags = ra.prm.flags | nocache;
+    kp->flags = prm.flags | nocache;
+}
+
+int make_kparams(sasa_b200_batch *b, const RunArgs &ra, KParams *kp) {
+    sasa_b200_ctx *ctx = b->ctx;
+    memset(kp, 0, sizeof *kp);
+    kp->xyzr = ra.d_xyzr;
+    kp->cls = ra.d_cls;
+    kp->struct_off = b->d_off;
+    kp->seg_be = b->d_seg_be;
+    kp->struct_seg_off = b->d_seg_off;
+    kp->seg_polar = b->d_polar;
+    kp->out_counts = ra.d_out.counts;
+    kp->out_atom = ra.d_out.atom_sasa;
+    kp->out_seg = b->n_seg ? ra.d_out.seg_sasa : nullptr;
+    kp->out_protein = ra.d_out.protein;
+    fill_run_params(kp, ra.pts, ra.prm);
     kp->err_flag = ctx->d_err;
     kp->stat = ctx->d_stat;
     return SASA_B200_OK;
@@ -553,6 +594,8 @@ int sasa_b200_create(int device, sasa_b200_ctx **out_ctx) {
     }
     if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_large, cudaEventDisableTiming)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaEventCreate", e);
+    for (int i = 0; i < kStreams; ++i)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_tail[i], cudaEventDisableTiming)) != cudaSuccess) return bail(SASA_B200_ERR_CUDA, "cudaEventCreate", e);
     {   // per-batch topology arrays come from the stream-ordered pool: keep freed blocks cached instead of returning them
         cudaMemPool_t pool = nullptr;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
@@ -589,6 +632,20 @@ void sasa_b200_destroy(sasa_b200_ctx *ctx) {
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_large) cudaEventDestroy(ctx->ev_large);
+    for (int i = 0; i < kStreams; ++i)
+        if (ctx->ev_tail[i]) cudaEventDestroy(ctx->ev_tail[i]);
+    for (sasa_b200_job *j : ctx->free_jobs) {
+        cudaEventDestroy(j->ev0);
+        cudaEventDestroy(j->ev1);
+        cudaFreeHost(j->h_status);
+        delete j;
+    }
+    for (auto &sp : ctx->slots) {
+        if (sp->st) cudaStreamDestroy(sp->st);
+        large_release(sp->large);
+        cudaFree(sp->d_buf);
+        cudaFreeHost(sp->h_pin);
+    }
     large_release(ctx->large);
     cudaFree(ctx->d_err);
     cudaFree(ctx->d_stat);
@@ -760,17 +817,54 @@ int sasa_b200_batch_sync(sasa_b200_batch *b, sasa_b200_stats *stats) {
     return rc;
 }
 
-static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz3, const float *radii,
-                         const uint32_t *id_class, const sasa_b200_params *params, const sasa_b200_outputs *out,
-                         sasa_b200_stats *stats) {
+// ---- host-buffer runs as jobs ---------------------------------------------------------------------------------------
+// submit: everything of one run is enqueued -- H2D copies, kernels, D2H copies into the caller's buffers, chunk by chunk on
+// three streams -- and the call returns; wait: blocks on the job's last event and reports.  The context mutex is held only
+// while enqueueing, so callers on several threads interleave their jobs instead of queueing for whole runs.  A job owns a
+// stream-ordered arena (cudaMallocAsync; the pool keeps freed blocks) and its own error / statistics words.
+static sasa_b200_job *job_acquire(sasa_b200_ctx *ctx) {
+    sasa_b200_job *j = nullptr;
+    if (!ctx->free_jobs.empty()) {
+        j = ctx->free_jobs.back();
+        ctx->free_jobs.pop_back();
+    } else {
+        j = new sasa_b200_job();
+        if (cudaEventCreate(&j->ev0) != cudaSuccess || cudaEventCreate(&j->ev1) != cudaSuccess ||
+            cudaHostAlloc((void **)&j->h_status, 4 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) {
+            if (j->ev0) cudaEventDestroy(j->ev0);
+            if (j->ev1) cudaEventDestroy(j->ev1);
+            delete j;
+            return nullptr;
+        }
+    }
+    return j;
+}
+
+// Failure after work was queued: nothing may still write into the caller's buffers or read the arena once the call returns.
+static int job_abort(sasa_b200_ctx *ctx, sasa_b200_job *j, int rc) {
+    for (int i = 0; i < kStreams; ++i) cudaStreamSynchronize(ctx->streams[i]);
+    if (j->d_arena) cudaFreeAsync(j->d_arena, ctx->streams[0]);
+    j->d_arena = nullptr;
+    if (j->batch) j->batch->in_flight = nullptr;
+    j->active = false;
+    ctx->tail_valid = false;
+    ctx->free_jobs.push_back(j);
+    cudaGetLastError();
+    return rc;
+}
+
+static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz3, const float *radii,
+                            const uint32_t *id_class, const sasa_b200_params *params, const sasa_b200_outputs *out,
+                            sasa_b200_job **out_job) {
     sasa_b200_ctx *ctx = b->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    if (!out) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "out is NULL");
+    if (!out || !out_job) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "out / out_job is NULL");
+    *out_job = nullptr;
     if (b->n_atoms && !xyzr && !(xyz3 && radii)) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "atom data is NULL");
+    if (b->in_flight) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "this batch already has a run in flight: wait for it first");
     int rc = check_params(ctx, params);
     if (rc) return rc;
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const auto t_begin = std::chrono::steady_clock::now();
     const size_t N = b->n_atoms, S = b->S, G = b->n_seg;
     const int variant = id_class ? 1 : 0;
     const bool frames = xyz3 != nullptr;
@@ -781,9 +875,17 @@ static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz
             if (b->h_off[s + 1] - b->h_off[s] != fN)
                 return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "run_frames needs equal-sized structures");
     }
+    const Points *pts = nullptr;
+    if ((rc = get_points(ctx, params->n_points, &pts)) != 0) return rc;
+    sasa_b200_job *job = job_acquire(ctx);
+    if (!job) return fail(ctx, SASA_B200_ERR_CUDA, "creating the job's events / status word failed");
+    job->batch = b;
+    job->t_begin = std::chrono::steady_clock::now();
+    job->launches = 0;
     // carve the arena
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o = 0;
+    const size_t o_status = o; o += 256;
     const size_t o_xyzr = o;   o += al(N * 16);
     const size_t o_xyz3 = o;   o += frames ? al(N * 12) : 0;
     const size_t o_rad = o;    o += frames ? al(fN * 4) : 0;
@@ -792,8 +894,29 @@ static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz
     const size_t o_atom = o;   o += out->atom_sasa ? al(N * 4) : 0;
     const size_t o_seg = o;    o += (out->seg_sasa && G) ? al(G * 4) : 0;
     const size_t o_prot = o;   o += out->protein ? al(S * 12) : 0;
-    if ((rc = arena_reserve(ctx, o + 256)) != 0) return rc;
-    char *base_p = static_cast<char *>(ctx->arena);
+    cudaStream_t s0 = ctx->streams[0];
+    // the previous job may still be running on the sibling streams: this job's first stream starts behind all of them
+    if (ctx->tail_valid)
+        for (int i = 1; i < kStreams; ++i) cudaStreamWaitEvent(s0, ctx->ev_tail[i], 0);
+    {
+        cudaError_t e = cudaMallocAsync(&job->d_arena, o + 256, s0);
+        if (e != cudaSuccess) {
+            job->d_arena = nullptr;
+            job_abort(ctx, job, 0);
+            return fail(ctx, e == cudaErrorMemoryAllocation ? SASA_B200_ERR_OUT_OF_MEMORY : SASA_B200_ERR_CUDA,
+                        "cudaMallocAsync(%zu) failed: %s", o + 256, cudaGetErrorString(e));
+        }
+    }
+    b->in_flight = job;
+    job->active = true;
+#define J_TRY(expr)                                                                                                       \
+    do {                                                                                                                  \
+        cudaError_t e__ = (expr);                                                                                         \
+        if (e__ != cudaSuccess)                                                                                           \
+            return job_abort(ctx, job, fail(ctx, e__ == cudaErrorMemoryAllocation ? SASA_B200_ERR_OUT_OF_MEMORY : SASA_B200_ERR_CUDA, \
+                                            "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+    } while (0)
+    char *base_p = static_cast<char *>(job->d_arena);
     RunArgs ra;
     ra.d_xyzr = reinterpret_cast<const float4 *>(base_p + o_xyzr);
     ra.d_cls = id_class ? reinterpret_cast<const uint32_t *>(base_p + o_cls) : nullptr;
@@ -802,10 +925,12 @@ static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz
     ra.d_out.seg_sasa = (out->seg_sasa && G) ? reinterpret_cast<float *>(base_p + o_seg) : nullptr;
     ra.d_out.protein = out->protein ? reinterpret_cast<float *>(base_p + o_prot) : nullptr;
     ra.prm = *params;
-    if ((rc = get_points(ctx, params->n_points, &ra.pts)) != 0) return rc;
+    ra.pts = pts;
     KParams kbase;
     make_kparams(b, ra, &kbase);
-    b->launches_last = 0;
+    unsigned long long *d_status = reinterpret_cast<unsigned long long *>(base_p + o_status);
+    kbase.err_flag = reinterpret_cast<int *>(d_status);
+    kbase.stat = d_status + 1;
     // MD form: the fused kernels read the 12-byte coordinates and the shared radius table directly; only batches with
     // structures on the large-structure path still expand to float4 first
     const bool fused_frames = frames && b->max_large == 0;
@@ -813,16 +938,11 @@ static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz
         kbase.xyz3 = reinterpret_cast<const float *>(base_p + o_xyz3);
         kbase.radii = reinterpret_cast<const float *>(base_p + o_rad);
     }
-
-    cudaEvent_t ev0, ev1;
-    CU_TRY(ctx, cudaEventCreate(&ev0));
-    CU_TRY(ctx, cudaEventCreate(&ev1));
-    if (b->n_counters[variant])
-        CU_TRY(ctx, cudaMemsetAsync(b->d_counters, 0, b->n_counters[variant] * sizeof(uint32_t), ctx->streams[0]));
-    if (frames && fN)
-        CU_TRY(ctx, cudaMemcpyAsync(base_p + o_rad, radii, fN * 4, cudaMemcpyHostToDevice, ctx->streams[0]));
-    CU_TRY(ctx, cudaEventRecord(ev0, ctx->streams[0]));
-    for (int i = 1; i < kStreams; ++i) CU_TRY(ctx, cudaStreamWaitEvent(ctx->streams[i], ev0, 0));
+    J_TRY(cudaMemsetAsync(d_status, 0, 32, s0));
+    if (b->n_counters[variant]) J_TRY(cudaMemsetAsync(b->d_counters, 0, b->n_counters[variant] * sizeof(uint32_t), s0));
+    if (frames && fN) J_TRY(cudaMemcpyAsync(base_p + o_rad, radii, fN * 4, cudaMemcpyHostToDevice, s0));
+    J_TRY(cudaEventRecord(job->ev0, s0));
+    for (int i = 1; i < kStreams; ++i) J_TRY(cudaStreamWaitEvent(ctx->streams[i], job->ev0, 0));
     size_t ci = 0;
     // the large-structure workspace is shared by all chunks: keep such batches on a single stream
     const int nstreams = b->max_large ? 1 : kStreams;
@@ -831,42 +951,103 @@ static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz
         const size_t na = ch.a1 - ch.a0;
         if (na) {
             if (frames) {
-                CU_TRY(ctx, cudaMemcpyAsync(base_p + o_xyz3 + ch.a0 * 12, xyz3 + ch.a0 * 3, na * 12, cudaMemcpyHostToDevice, st));
-                if (!fused_frames) pack_frames_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(
-                    reinterpret_cast<const float *>(base_p + o_xyz3) + ch.a0 * 3, reinterpret_cast<const float *>(base_p + o_rad),
-                    reinterpret_cast<float4 *>(base_p + o_xyzr) + ch.a0, (uint32_t)na, (uint32_t)fN, (uint32_t)(ch.a0 % (fN ? fN : 1)));
-                if (!fused_frames) ++b->launches_last;
+                J_TRY(cudaMemcpyAsync(base_p + o_xyz3 + ch.a0 * 12, xyz3 + ch.a0 * 3, na * 12, cudaMemcpyHostToDevice, st));
+                if (!fused_frames) {
+                    pack_frames_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(
+                        reinterpret_cast<const float *>(base_p + o_xyz3) + ch.a0 * 3, reinterpret_cast<const float *>(base_p + o_rad),
+                        reinterpret_cast<float4 *>(base_p + o_xyzr) + ch.a0, (uint32_t)na, (uint32_t)fN, (uint32_t)(ch.a0 % (fN ? fN : 1)));
+                    ++job->launches;
+                }
             } else {
-                CU_TRY(ctx, cudaMemcpyAsync(base_p + o_xyzr + ch.a0 * 16, xyzr + ch.a0 * 4, na * 16, cudaMemcpyHostToDevice, st));
+                J_TRY(cudaMemcpyAsync(base_p + o_xyzr + ch.a0 * 16, xyzr + ch.a0 * 4, na * 16, cudaMemcpyHostToDevice, st));
             }
-            if (id_class)
-                CU_TRY(ctx, cudaMemcpyAsync(base_p + o_cls + ch.a0 * 4, id_class + ch.a0, na * 4, cudaMemcpyHostToDevice, st));
+            if (id_class) J_TRY(cudaMemcpyAsync(base_p + o_cls + ch.a0 * 4, id_class + ch.a0, na * 4, cudaMemcpyHostToDevice, st));
         }
-        if ((rc = enqueue_chunk(b, variant, ch, kbase, st, &b->launches_last)) != 0) return rc;
+        if ((rc = enqueue_chunk(b, variant, ch, kbase, st, &job->launches)) != 0) return job_abort(ctx, job, rc);
         if (na && out->counts)
-            CU_TRY(ctx, cudaMemcpyAsync(out->counts + ch.a0, base_p + o_cnt + ch.a0 * 4, na * 4, cudaMemcpyDeviceToHost, st));
+            J_TRY(cudaMemcpyAsync(out->counts + ch.a0, base_p + o_cnt + ch.a0 * 4, na * 4, cudaMemcpyDeviceToHost, st));
         if (na && out->atom_sasa)
-            CU_TRY(ctx, cudaMemcpyAsync(out->atom_sasa + ch.a0, base_p + o_atom + ch.a0 * 4, na * 4, cudaMemcpyDeviceToHost, st));
+            J_TRY(cudaMemcpyAsync(out->atom_sasa + ch.a0, base_p + o_atom + ch.a0 * 4, na * 4, cudaMemcpyDeviceToHost, st));
         if (out->seg_sasa && ch.g1 > ch.g0)
-            CU_TRY(ctx, cudaMemcpyAsync(out->seg_sasa + ch.g0, base_p + o_seg + ch.g0 * 4, (ch.g1 - ch.g0) * 4, cudaMemcpyDeviceToHost, st));
+            J_TRY(cudaMemcpyAsync(out->seg_sasa + ch.g0, base_p + o_seg + ch.g0 * 4, (ch.g1 - ch.g0) * 4, cudaMemcpyDeviceToHost, st));
         if (out->protein && ch.s1 > ch.s0)
-            CU_TRY(ctx, cudaMemcpyAsync(out->protein + 3 * (size_t)ch.s0, base_p + o_prot + 12 * (size_t)ch.s0,
-                                        12 * (size_t)(ch.s1 - ch.s0), cudaMemcpyDeviceToHost, st));
+            J_TRY(cudaMemcpyAsync(out->protein + 3 * (size_t)ch.s0, base_p + o_prot + 12 * (size_t)ch.s0,
+                                  12 * (size_t)(ch.s1 - ch.s0), cudaMemcpyDeviceToHost, st));
     }
-    for (int i = 0; i < kStreams; ++i) CU_TRY(ctx, cudaStreamSynchronize(ctx->streams[i]));
-    CU_TRY(ctx, cudaEventRecord(ev1, ctx->streams[0]));
-    CU_TRY(ctx, cudaEventSynchronize(ev1));
-    float ms = 0.0f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    b->last = sasa_b200_stats{};
-    b->last.kernel_ms = ms;  // device-side span of the whole pipelined run (copies overlapped with kernels)
-    b->last.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-    rc = finish_run(b, stats);
-    cudaMemset(ctx->d_err, 0, sizeof(int));
-    cudaMemset(ctx->d_stat, 0, 3 * sizeof(unsigned long long));
+    // join the sibling streams into the first one, read the status words back, free the arena in stream order
+    for (int i = 1; i < kStreams; ++i) {
+        J_TRY(cudaEventRecord(ctx->ev_tail[i], ctx->streams[i]));
+        J_TRY(cudaStreamWaitEvent(s0, ctx->ev_tail[i], 0));
+    }
+    ctx->tail_valid = true;
+    J_TRY(cudaMemcpyAsync(job->h_status, d_status, 32, cudaMemcpyDeviceToHost, s0));
+    J_TRY(cudaEventRecord(job->ev1, s0));
+    J_TRY(cudaFreeAsync(job->d_arena, s0));
+    job->d_arena = nullptr;
+#undef J_TRY
+    *out_job = job;
+    return SASA_B200_OK;
+}
+
+static int wait_job_impl(sasa_b200_job *job, sasa_b200_stats *stats) {
+    sasa_b200_batch *b = job->batch;
+    sasa_b200_ctx *ctx = b->ctx;
+    cudaError_t e = cudaEventSynchronize(job->ev1);   // no lock: other threads keep submitting meanwhile
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = SASA_B200_OK;
+    if (e != cudaSuccess) {
+        rc = fail(ctx, SASA_B200_ERR_CUDA, "waiting for the run failed: %s", cudaGetErrorString(e));
+    } else {
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, job->ev0, job->ev1);
+        b->last = sasa_b200_stats{};
+        b->last.kernel_ms = ms;   // device-side span of the whole pipelined run (copies overlapped with kernels)
+        b->last.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - job->t_begin).count();
+        b->last.n_atoms = b->n_atoms;
+        b->last.n_structures = b->S;
+        b->last.boundary_points = job->h_status[1];
+        b->last.neighbor_pairs = job->h_status[2];
+        b->last.streamed_atoms = job->h_status[3];
+        b->last.gpu_launches = job->launches;
+        b->launches_last = job->launches;
+        if (stats) *stats = b->last;
+        const int h_err = (int)(job->h_status[0] & 0xffffffffull);
+        if (h_err == SASA_B200_ERR_NON_FINITE)
+            rc = fail(ctx, SASA_B200_ERR_NON_FINITE, "non-finite coordinate or radius in the input (the reference panics here)");
+        else if (h_err)
+            rc = fail(ctx, h_err, "device-side error %d", h_err);
+    }
+    b->in_flight = nullptr;
+    job->active = false;
+    ctx->free_jobs.push_back(job);
     return rc;
+}
+
+static int run_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz3, const float *radii,
+                         const uint32_t *id_class, const sasa_b200_params *params, const sasa_b200_outputs *out,
+                         sasa_b200_stats *stats) {
+    sasa_b200_job *job = nullptr;
+    int rc = submit_host_impl(b, xyzr, xyz3, radii, id_class, params, out, &job);
+    if (rc) return rc;
+    return wait_job_impl(job, stats);
+}
+
+int sasa_b200_batch_submit_host(sasa_b200_batch *b, const float *xyzr, const uint32_t *id_class, const sasa_b200_params *params,
+                                const sasa_b200_outputs *out, sasa_b200_job **out_job) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    return submit_host_impl(b, xyzr, nullptr, nullptr, id_class, params, out, out_job);
+}
+
+int sasa_b200_batch_submit_frames_host(sasa_b200_batch *b, const float *xyz, const float *radii, const sasa_b200_params *params,
+                                       const sasa_b200_outputs *out, sasa_b200_job **out_job) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    if (!xyz || !radii) return fail(b->ctx, SASA_B200_ERR_INVALID_ARGUMENT, "xyz / radii is NULL");
+    return submit_host_impl(b, nullptr, xyz, radii, nullptr, params, out, out_job);
+}
+
+int sasa_b200_job_wait(sasa_b200_job *job, sasa_b200_stats *stats) {
+    if (!job || !job->active) return SASA_B200_ERR_INVALID_ARGUMENT;
+    return wait_job_impl(job, stats);
 }
 
 int sasa_b200_batch_run_host(sasa_b200_batch *b, const float *xyzr, const uint32_t *id_class,
@@ -996,9 +1177,185 @@ int sasa_b200_batch_reduce_device(sasa_b200_batch *b, const float *d_atom_sasa, 
     return SASA_B200_OK;
 }
 
+// ---- one structure per call ---------------------------------------------------------------------------------------------
+// What SASAOptions::process does in the reference: one structure, host buffers, synchronous (BASELINE config 1).  The call
+// takes a slot -- stream, large-structure workspace, device buffer and pinned staging of its own -- so that concurrent
+// callers (the reference's directory mode, src/main.rs:375, :439) overlap instead of queueing on the context; the
+// structure goes down the multi-CTA large-structure path (a lone structure in a fused kernel would occupy one SM), and
+// inputs / outputs / status each travel in ONE copy.  About a dozen runtime calls in all.
+static SingleSlot *slot_acquire(sasa_b200_ctx *ctx) {
+    std::unique_lock<std::mutex> lk(ctx->slot_mu);
+    for (;;) {
+        for (auto &sp : ctx->slots)
+            if (!sp->busy) {
+                sp->busy = true;
+                return sp.get();
+            }
+        if (ctx->slots.size() < kMaxSlots) {
+            auto sp = std::make_unique<SingleSlot>();
+            if (cudaStreamCreateWithFlags(&sp->st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            sp->busy = true;
+            ctx->slots.push_back(std::move(sp));
+            return ctx->slots.back().get();
+        }
+        ctx->slot_cv.wait(lk);
+    }
+}
+
+static void slot_release(sasa_b200_ctx *ctx, SingleSlot *sl) {
+    {
+        std::lock_guard<std::mutex> lk(ctx->slot_mu);
+        sl->busy = false;
+    }
+    ctx->slot_cv.notify_one();
+}
+
+static int single_run(sasa_b200_ctx *ctx, const float *xyzr, const uint32_t *cls, size_t N, const uint32_t *seg_be, size_t G,
+                      const uint8_t *seg_polar, const sasa_b200_params *params, const sasa_b200_outputs *out,
+                      sasa_b200_stats *stats, std::string *err_text) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    const Points *pts = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        int rc = check_params(ctx, params);
+        if (rc == 0) rc = get_points(ctx, params->n_points, &pts);
+        if (rc) {
+            *err_text = ctx->err;
+            return rc;
+        }
+    }
+    auto failed = [&](int code, const char *what, cudaError_t e) {
+        *err_text = std::string(what) + ": " + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? (int)SASA_B200_ERR_OUT_OF_MEMORY : code;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return failed(SASA_B200_ERR_CUDA, "cudaSetDevice", e);
+    SingleSlot *sl = slot_acquire(ctx);
+    if (!sl) return failed(SASA_B200_ERR_CUDA, "creating a slot stream", cudaGetLastError());
+    struct Release {
+        sasa_b200_ctx *c;
+        SingleSlot *s;
+        ~Release() { slot_release(c, s); }
+    } release{ctx, sl};
+    // layout (offsets shared by the device buffer and the pinned staging): inputs | outputs | status
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const bool segs = seg_be != nullptr && G > 0;
+    size_t o = 0;
+    const size_t o_xyzr = o;  o += al(N * 16);
+    const size_t o_cls = o;   o += cls ? al(N * 4) : 0;
+    const size_t o_seg = o;   o += segs ? al(G * 8) : 0;
+    const size_t o_pol = o;   o += (segs && seg_polar) ? al(G) : 0;
+    const size_t o_off = o;   o += 256;   // struct_off {0, N}, struct_seg_off {0, G}
+    const size_t in_bytes = o;
+    const size_t o_atom = o;  o += out->atom_sasa ? al(N * 4) : 0;
+    const size_t o_cnt = o;   o += out->counts ? al(N * 4) : 0;
+    const size_t o_sseg = o;  o += (segs && out->seg_sasa) ? al(G * 4) : 0;
+    const size_t o_prot = o;  o += out->protein ? 256 : 0;
+    const size_t out_bytes = o - in_bytes;
+    const size_t o_hdr = o;   o += al(sizeof(LargeHeader));
+    if (o > sl->d_bytes) {
+        cudaStreamSynchronize(sl->st);
+        cudaFree(sl->d_buf);
+        cudaFreeHost(sl->h_pin);
+        sl->d_buf = nullptr; sl->h_pin = nullptr; sl->d_bytes = sl->h_bytes = 0;
+        const size_t want = o + o / 4 + (64 << 10);
+        if ((e = cudaMalloc((void **)&sl->d_buf, want)) != cudaSuccess) return failed(SASA_B200_ERR_CUDA, "cudaMalloc", e);
+        if ((e = cudaHostAlloc((void **)&sl->h_pin, want, cudaHostAllocDefault)) != cudaSuccess) return failed(SASA_B200_ERR_CUDA, "cudaHostAlloc", e);
+        sl->d_bytes = sl->h_bytes = want;
+    }
+    if (N > sl->large.cap_atoms) {
+        cudaStreamSynchronize(sl->st);
+        if (large_reserve(sl->large, (uint32_t)std::max<size_t>(N + N / 4, 4096)) != 0) {
+            *err_text = "allocating the large-structure workspace failed";
+            return SASA_B200_ERR_OUT_OF_MEMORY;
+        }
+    }
+    char *h = sl->h_pin, *d = sl->d_buf;
+    memcpy(h + o_xyzr, xyzr, N * 16);
+    if (cls) memcpy(h + o_cls, cls, N * 4);
+    if (segs) memcpy(h + o_seg, seg_be, G * 8);
+    if (segs && seg_polar) memcpy(h + o_pol, seg_polar, G);
+    {
+        uint32_t *off = reinterpret_cast<uint32_t *>(h + o_off);
+        off[0] = 0; off[1] = (uint32_t)N; off[2] = 0; off[3] = (uint32_t)G;
+    }
+    if ((e = cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, sl->st)) != cudaSuccess) return failed(SASA_B200_ERR_CUDA, "H2D copy", e);
+    KParams kp;
+    memset(&kp, 0, sizeof kp);
+    kp.xyzr = reinterpret_cast<const float4 *>(d + o_xyzr);
+    kp.cls = cls ? reinterpret_cast<const uint32_t *>(d + o_cls) : nullptr;
+    kp.struct_off = reinterpret_cast<const uint32_t *>(d + o_off);
+    if (segs) {
+        kp.seg_be = reinterpret_cast<const uint2 *>(d + o_seg);
+        kp.struct_seg_off = reinterpret_cast<const uint32_t *>(d + o_off) + 2;
+        kp.seg_polar = seg_polar ? reinterpret_cast<const uint8_t *>(d + o_pol) : nullptr;
+    }
+    kp.out_atom = out->atom_sasa ? reinterpret_cast<float *>(d + o_atom) : nullptr;
+    kp.out_counts = out->counts ? reinterpret_cast<uint32_t *>(d + o_cnt) : nullptr;
+    kp.out_seg = (segs && out->seg_sasa) ? reinterpret_cast<float *>(d + o_sseg) : nullptr;
+    kp.out_protein = out->protein ? reinterpret_cast<float *>(d + o_prot) : nullptr;
+    fill_run_params(&kp, pts, *params);
+    kp.err_flag = &sl->large.hdr->err;
+    kp.stat = sl->large.hdr->stat;
+    const uint32_t order[1] = {0}, offs[2] = {0, (uint32_t)N}, soff[2] = {0, (uint32_t)G};
+    uint32_t launches = 0;
+    int rc = large_enqueue(ctx->sm_count, sl->large, kp, order, 1, offs, segs ? soff : nullptr, sl->st, &launches);
+    if (rc) {
+        cudaStreamSynchronize(sl->st);
+        *err_text = std::string("large-structure path failed: ") + cudaGetErrorString(cudaGetLastError());
+        return rc;
+    }
+    if (out_bytes && (e = cudaMemcpyAsync(h + in_bytes, d + in_bytes, out_bytes, cudaMemcpyDeviceToHost, sl->st)) != cudaSuccess)
+        return failed(SASA_B200_ERR_CUDA, "D2H copy", e);
+    if ((e = cudaMemcpyAsync(h + o_hdr, sl->large.hdr, sizeof(LargeHeader), cudaMemcpyDeviceToHost, sl->st)) != cudaSuccess)
+        return failed(SASA_B200_ERR_CUDA, "D2H copy", e);
+    if ((e = cudaStreamSynchronize(sl->st)) != cudaSuccess) return failed(SASA_B200_ERR_CUDA, "cudaStreamSynchronize", e);
+    if (out->atom_sasa) memcpy(out->atom_sasa, h + o_atom, N * 4);
+    if (out->counts) memcpy(out->counts, h + o_cnt, N * 4);
+    if (segs && out->seg_sasa) memcpy(out->seg_sasa, h + o_sseg, G * 4);
+    if (out->protein) memcpy(out->protein, h + o_prot, 12);
+    const LargeHeader *hh = reinterpret_cast<const LargeHeader *>(h + o_hdr);
+    if (stats) {
+        *stats = sasa_b200_stats{};
+        stats->n_atoms = N;
+        stats->n_structures = 1;
+        stats->boundary_points = hh->stat[0];
+        stats->neighbor_pairs = hh->stat[1];
+        stats->streamed_atoms = hh->stat[2];
+        stats->gpu_launches = launches;
+        stats->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    }
+    if (hh->err == SASA_B200_ERR_NON_FINITE) {
+        *err_text = "non-finite coordinate or radius in the input (the reference panics here)";
+        return SASA_B200_ERR_NON_FINITE;
+    }
+    if (hh->err) {
+        *err_text = "device-side error " + std::to_string(hh->err);
+        return hh->err;
+    }
+    return SASA_B200_OK;
+}
+
 int sasa_b200_run_batch(sasa_b200_ctx *ctx, const float *xyzr, const uint32_t *id_class, const uint64_t *struct_off,
                         size_t S, const uint32_t *seg_be, const uint64_t *struct_seg_off, const uint8_t *seg_polar,
                         const sasa_b200_params *params, const sasa_b200_outputs *out, sasa_b200_stats *stats) {
+    if (!ctx) return SASA_B200_ERR_INVALID_ARGUMENT;
+    if (S == 1 && struct_off && struct_off[0] == 0 && struct_off[1] > 0 && struct_off[1] < (1ull << 31) && xyzr && out && params &&
+        (!seg_be || struct_seg_off)) {
+        const size_t N = (size_t)struct_off[1];
+        const size_t G = seg_be ? (size_t)(struct_seg_off[1] - struct_seg_off[0]) : 0;
+        bool ok = !seg_be || struct_seg_off[0] == 0;
+        for (size_t k = 0; ok && k < G; ++k) ok = seg_be[2 * k] <= seg_be[2 * k + 1] && seg_be[2 * k + 1] <= N;
+        if (ok) {
+            std::string text;
+            const int rc = single_run(ctx, xyzr, id_class, N, seg_be, G, seg_polar, params, out, stats, &text);
+            if (rc) {
+                std::lock_guard<std::mutex> lk(ctx->mu);
+                ctx->err = text;
+            }
+            return rc;
+        }
+    }
     sasa_b200_batch *b = nullptr;
     int rc = batch_create_impl(ctx, struct_off, S, seg_be, struct_seg_off, seg_polar, &b, S == 1);
     if (rc) return rc;

@@ -22,7 +22,9 @@ struct LargeHeader {
     unsigned enc[8];        // maxima of order-preserving encodings: -min xyz [0..2], max xyz [3..5], r_max [6]; [7] = non-finite flag
     unsigned next_block;    // work counter of the atoms kernels: next owned work block
     unsigned tile_counter;  // scan kernel: next tile
-    unsigned pad[2];
+    int err;                // error flag / statistics of runs that own their workspace (the one-structure calls): zeroed with the
+    unsigned pad;           // rest of the header, copied back with the results
+    unsigned long long stat[4];
     Grid grid;              // written by the count kernel (every block derives the same grid from enc[])
     int ncell;              // 0: non-finite input, nothing to evaluate
     unsigned pad2[3];
@@ -30,7 +32,8 @@ struct LargeHeader {
 static_assert(sizeof(LargeHeader) % 16 == 0, "header is followed by 16-byte aligned arrays");
 
 constexpr int kScanItems = 2048;   // cells per scan tile (256 threads x 8)
-constexpr int kLBlock = 8;         // atoms per work block of the atoms kernels (blocks are cut at cell boundaries)
+constexpr int kLBlock = 8;         // most atoms per work block of the atoms kernels (blocks are cut at cell boundaries); structures too
+                                   // small to give every resident warp such a block use smaller ones (large_block_atoms)
 constexpr int kLGroup = 4;         // consecutive work blocks owned by one rank in the atom-range split
 
 struct LargeWorkspace {
@@ -148,11 +151,11 @@ __global__ void __launch_bounds__(256) large_count_kernel(const float4 *__restri
 // atomic counter, so a tile's predecessors are always resident or finished).  cells[ncell] = N.  Tile state (u64, zeroed by
 // the workspace memset): bits 62-63 = 1 aggregate known / 2 inclusive prefix known, low bits the value.
 // The same pass cuts the cell-sorted order into the work blocks of the atoms kernels: bstart[b] = first cell start at or
-// after atom b * kLBlock -- emitted by the cell in front of that start -- and bstart[ceil(N / kLBlock)] = N.  Cell starts
+// after atom b * blk -- emitted by the cell in front of that start -- and bstart[ceil(N / blk)] = N.  Cell starts
 // are the same on every GPU (the order of atoms INSIDE a cell is not: it comes from atomics), so blocks partition the atoms
 // identically on every rank of an atom-range split.
 __global__ void __launch_bounds__(256) large_scan_kernel(LargeHeader *h, uint32_t *cells, unsigned long long *tiles, uint32_t *bstart,
-                                                         uint32_t N) {
+                                                         uint32_t N, uint32_t blk) {
     const int n = h->ncell;
     __shared__ unsigned s_tile;
     __shared__ uint32_t wsum[8];
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(256) large_scan_kernel(LargeHeader *h, uint32_
                 cells[t0 + k] = run;
                 if (v[k]) {   // the next cell starts at run + v[k]: it is the first start at or after every block target in (run, run + v[k]]
                     const uint32_t nxt = run + v[k];
-                    for (uint32_t b = run / kLBlock + 1; b * kLBlock <= nxt; ++b) bstart[b] = nxt;
+                    for (uint32_t b = run / blk + 1; b * blk <= nxt; ++b) bstart[b] = nxt;
                 }
             }
             run += v[k];
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(256) large_scan_kernel(LargeHeader *h, uint32_
         if (tile == ntiles - 1 && threadIdx.x == 255) {
             cells[n] = N;
             bstart[0] = 0u;
-            bstart[(N + kLBlock - 1) / kLBlock] = N;
+            bstart[(N + blk - 1) / blk] = N;
         }
     }
 }
@@ -393,7 +396,7 @@ template <int NCHP>
 __global__ void __launch_bounds__(256, 4) large_cells_kernel(const KParams p, int N, uint32_t a0, LargeHeader *h,
                                                              const float4 *__restrict__ sorted, const uint32_t *__restrict__ orig,
                                                              const uint32_t *__restrict__ cells, const uint32_t *__restrict__ bstart,
-                                                             float *val, uint32_t rank, uint32_t n_ranks) {
+                                                             float *val, uint32_t rank, uint32_t n_ranks, uint32_t blk) {
     static_assert(kLCap * 16 >= kNbCap * 16 + kNbCap * 4 + 64, "the cold path's scratch must fit the staging strip");
     __shared__ __align__(16) float4 s_stage[8][kLCap];
     __shared__ __align__(16) uint32_t s_nbp[8][kLNb];
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(256, 4) large_cells_kernel(const KParams p, in
         }
         __syncthreads();
     }
-    const unsigned nblocks = ((unsigned)N + kLBlock - 1) / kLBlock;
+    const unsigned nblocks = ((unsigned)N + blk - 1) / blk;
     const float reach0 = 2.0f * p.probe + kCutSlack;
     unsigned long long pairs = 0;
     int streamed = 0;
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
                                                              const float4 *__restrict__ sorted, const uint32_t *__restrict__ orig,
                                                              const uint32_t *__restrict__ cls_sorted, const uint32_t *__restrict__ cells,
                                                              const uint32_t *__restrict__ bstart, float *val, uint32_t rank,
-                                                             uint32_t n_ranks) {
+                                                             uint32_t n_ranks, uint32_t blk) {
     __shared__ __align__(16) float4 s_ent[8 * kNbCap];
     __shared__ uint32_t s_cand[8 * kNbCap];       // u32 candidate positions; reused as the u16 survivor queue
     static_assert(kNbCap * 2 >= kQueueCap, "survivor queue must fit the candidate list");
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
                                           v ? __ldg(p.pz + threadIdx.x) : 0.f, 0.f);
     }
     __syncthreads();
-    const unsigned nblocks = ((unsigned)N + kLBlock - 1) / kLBlock;
+    const unsigned nblocks = ((unsigned)N + blk - 1) / blk;
     CandCache<uint32_t> cc;
     for (;;) {
         unsigned t = 0;
@@ -729,7 +732,7 @@ inline int large_reserve(LargeWorkspace &w, uint32_t n_atoms) {
     if (cudaMalloc(&w.sorted, (size_t)n_atoms * 16) != cudaSuccess || cudaMalloc(&w.orig, (size_t)n_atoms * 4) != cudaSuccess ||
         cudaMalloc(&w.cellid, (size_t)n_atoms * 4) != cudaSuccess || cudaMalloc(&w.rank, (size_t)n_atoms * 4) != cudaSuccess ||
         cudaMalloc(&w.cls_sorted, (size_t)n_atoms * 4) != cudaSuccess || cudaMalloc(&w.val, (size_t)n_atoms * 4) != cudaSuccess ||
-        cudaMalloc(&w.bstart, ((size_t)n_atoms / kLBlock + 2) * 4) != cudaSuccess ||
+        cudaMalloc(&w.bstart, ((size_t)n_atoms + 2) * 4) != cudaSuccess ||
         cudaMalloc(&w.zero_block, sizeof(LargeHeader) + tiles_bytes + (want_cells + 2) * 4) != cudaSuccess) {
         large_release(w);
         return 3;  // SASA_B200_ERR_OUT_OF_MEMORY
@@ -771,23 +774,26 @@ inline int large_enqueue(int sm_count, LargeWorkspace &w, const KParams &kp, con
         const int gs = (int)std::max<size_t>(1, std::min<size_t>(large_tile_cap(cmax), (size_t)sm_count * 4));
         large_bounds_kernel<<<gb, 256, 0, st>>>(at, N, w.hdr);
         large_count_kernel<<<gc, 256, 0, st>>>(at, N, w.hdr, kp.probe, cmax, kp.err_flag, w.cells, w.cellid, w.rank);
-        large_scan_kernel<<<gs, 256, 0, st>>>(w.hdr, w.cells, w.tiles, w.bstart, (uint32_t)N);
-        large_scatter_kernel<<<gc, 256, 0, st>>>(at, cls, N, w.hdr, w.cells, w.cellid, w.rank, w.sorted, w.orig, w.cls_sorted);
+        // atoms per work block: kLBlock for structures that fill the machine, fewer for small ones so that every resident warp
+        // gets work (a 2,600-atom structure in blocks of 8 would occupy 7 % of the warp slots)
         const int owned = (int)(((uint64_t)N + range_n - 1) / range_n);
+        const uint32_t blk = (uint32_t)std::max(1, std::min(kLBlock, owned / (sm_count * 32)));
+        large_scan_kernel<<<gs, 256, 0, st>>>(w.hdr, w.cells, w.tiles, w.bstart, (uint32_t)N, blk);
+        large_scatter_kernel<<<gc, 256, 0, st>>>(at, cls, N, w.hdr, w.cells, w.cellid, w.rank, w.sorted, w.orig, w.cls_sorted);
         const bool table = (kp.n_points <= 128 && kp.cap) || (kp.n_points > 128 && kp.n_points <= 1024 && kp.capm_in);
         if (!cls && (kp.flags & 3u) == 0 && table) {
-            const int ga = std::max(1, std::min((owned + 8 * kLBlock - 1) / (8 * kLBlock), sm_count * 4));
+            const int ga = std::max(1, std::min((owned + 8 * (int)blk - 1) / (8 * (int)blk), sm_count * 4));
             const int shift = kp.n_points <= 128 ? 0 : kp.capd.nchp_shift;
-#define SASA_LARGE_CELLS(NCHP) large_cells_kernel<NCHP><<<ga, 256, 0, st>>>(kp, N, a0, w.hdr, w.sorted, w.orig, w.cells, w.bstart, w.val, range_rank, range_n)
+#define SASA_LARGE_CELLS(NCHP) large_cells_kernel<NCHP><<<ga, 256, 0, st>>>(kp, N, a0, w.hdr, w.sorted, w.orig, w.cells, w.bstart, w.val, range_rank, range_n, blk)
             if (shift == 0) SASA_LARGE_CELLS(1);
             else if (shift == 1) SASA_LARGE_CELLS(2);
             else if (shift == 2) SASA_LARGE_CELLS(4);
             else SASA_LARGE_CELLS(8);
 #undef SASA_LARGE_CELLS
         } else {
-            const int ga = std::max(1, std::min((owned + 8 * kLBlock - 1) / (8 * kLBlock), sm_count * 2));
+            const int ga = std::max(1, std::min((owned + 8 * (int)blk - 1) / (8 * (int)blk), sm_count * 2));
             large_atoms_kernel<<<ga, 256, 0, st>>>(kp, N, a0, w.hdr, w.sorted, w.orig, cls ? w.cls_sorted : nullptr, w.cells, w.bstart,
-                                                   w.val, range_rank, range_n);
+                                                   w.val, range_rank, range_n, blk);
         }
         *launches += 5;
         // level sums (not in the atom-range split, where the per-atom values of the other ranks are missing); the `rank`

@@ -195,6 +195,21 @@ class Batch:
         res.stats = st.as_dict()
         return res
 
+    def submit_host(self, xyzr, id_class=None, probe_radius=1.4, n_points=100, simd_lanes=8, flags=0,
+                    want=("counts", "atom", "seg", "protein"), result: Optional[BatchResult] = None) -> "Job":
+        """Asynchronous run_host: returns at once with a Job; `Job.wait()` blocks until the outputs are in host memory.
+        Inputs and outputs should be page-locked (``Engine.pinned_empty``) and must stay alive until wait returns."""
+        xyzr = _np(xyzr, np.float32, (-1, 4))
+        assert xyzr.shape[0] == self.n_atoms, "xyzr does not match struct_off"
+        id_class = _np(id_class, np.uint32)
+        res = result if result is not None else self._host_outputs(want, "pinned")
+        outs = _lib.Outputs(_ptr(res.counts), _ptr(res.atom_sasa), _ptr(res.seg_sasa), _ptr(res.protein))
+        prm = self._params(probe_radius, n_points, simd_lanes, flags)
+        h = C.c_void_p()
+        self.engine._check(self._L.sasa_b200_batch_submit_host(self._h, _ptr(xyzr), _ptr(id_class), C.byref(prm),
+                                                              C.byref(outs), C.byref(h)))
+        return Job(self, h, res, (xyzr, id_class))
+
     def run_frames_host(self, xyz, radii, probe_radius=1.4, n_points=100, simd_lanes=8, flags=0,
                         want=("protein",), result: Optional[BatchResult] = None) -> BatchResult:
         """MD form: xyz (F, N, 3) float32 + radii (N,) shared by all frames."""
@@ -251,3 +266,20 @@ class Batch:
         st = _lib.Stats()
         self.engine._check(self._L.sasa_b200_batch_sync(self._h, C.byref(st)))
         return st.as_dict()
+
+
+class Job:
+    """A host-buffer run in flight (sasa_b200_batch_submit_host .. sasa_b200_job_wait)."""
+
+    def __init__(self, batch: Batch, handle, result: BatchResult, keep):
+        self.batch, self._h, self.result, self._keep = batch, handle, result, keep
+
+    def wait(self) -> BatchResult:
+        if self._h is None:
+            return self.result
+        st = _lib.Stats()
+        h, self._h = self._h, None
+        self.batch.engine._check(self.batch._L.sasa_b200_job_wait(h, C.byref(st)))
+        self.result.stats = st.as_dict()
+        self._keep = None
+        return self.result

@@ -538,3 +538,124 @@ def test_large_path_non_finite_and_empty(eng):
     parts = [b.run_atom_range_host(a.xyzr, r, 2) for r in range(2)]
     assert np.array_equal(parts[0].atom_sasa + parts[1].atom_sasa, good)
     b.close()
+
+
+def test_submit_wait_jobs_overlap_and_match(eng, oracle, golden):
+    """sasa_b200_batch_submit_host / sasa_b200_job_wait: several jobs of different batches in flight at once, waited out of
+    order, equal the synchronous results; a second submit on a busy batch is refused."""
+    from rustsasa_b200 import SasaB200Error
+    from rustsasa_b200 import workloads as W
+    datas = [W.proteome_batch(24, seed=500 + i) for i in range(3)]
+    batches = [eng.batch(d.struct_off, d.seg_be, d.struct_seg_off, d.seg_polar) for d in datas]
+    pinned = []
+    for d in datas:
+        h = eng.pinned_empty((d.n_atoms, 4), np.float32)
+        h[...] = d.xyzr
+        pinned.append(h)
+    jobs = [b.submit_host(h) for b, h in zip(batches, pinned)]
+    with pytest.raises(SasaB200Error):
+        batches[0].submit_host(pinned[0])
+    for i in (2, 0, 1):
+        r = jobs[i].wait()
+        s = batches[i].run_host(datas[i].xyzr)
+        assert np.array_equal(np.asarray(r.counts), s.counts) and np.array_equal(np.asarray(r.seg_sasa), s.seg_sasa)
+        assert np.array_equal(np.asarray(r.protein), s.protein)
+        assert r.stats["gpu_launches"] >= 1 and r.stats["n_atoms"] == datas[i].n_atoms
+    # a non-finite value is reported by wait, and the batch is usable afterwards
+    bad = pinned[1].copy()
+    bad[5, 0] = np.nan
+    j = batches[1].submit_host(bad)
+    with pytest.raises(SasaB200Error) as ei:
+        j.wait()
+    assert ei.value.code == 4
+    again = batches[1].submit_host(pinned[1]).wait()
+    assert np.array_equal(np.asarray(again.counts), batches[1].run_host(datas[1].xyzr).counts)
+    for b in batches:
+        b.close()
+
+
+def test_concurrent_single_structure_callers(eng, oracle, golden):
+    """The reference's directory mode calls the engine from every worker thread (src/main.rs:375, :439): 16 threads calling
+    sasa_b200_calculate_sasa_internal on one context get correct results and overlap (each call has its own stream and
+    workspace), instead of queueing on a context-wide lock."""
+    import threading
+    import time
+    names = ["example.cif", "151L_H3.pdb", "2drt", "4xfj"]
+    xs = [golden.structure(n)["xyzr"] for n in names]
+    want = [oracle.calculate_sasa_internal(x, PROBE, 100) for x in xs]
+    for x in xs:
+        eng.calculate_sasa_internal(x)                      # warm the point set and one slot
+    reps = 60
+
+    def loop(tid, out):
+        ok = True
+        for r in range(reps):
+            k = (tid + r) % len(xs)
+            sasa, counts = eng.calculate_sasa_internal(xs[k], None, PROBE, 100, -1, want_counts=True)
+            ok = ok and np.array_equal(counts, want[k]["counts"]) and np.array_equal(sasa, want[k]["sasa"])
+        out[tid] = ok
+
+    def run(nthreads):
+        out = [False] * nthreads
+        th = [threading.Thread(target=loop, args=(t, out)) for t in range(nthreads)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        dt = time.perf_counter() - t0
+        assert all(out)
+        return nthreads * reps / dt
+
+    run(16)                                                  # creates the slots
+    single, many = run(1), run(16)
+    print(f"calls/s: 1 thread {single:.0f}, 16 threads {many:.0f} ({many / single:.1f}x)")
+    assert many > 1.5 * single                # python's GIL caps these threads; the C++ callers below are the measurement
+
+
+def test_concurrent_callers_from_cpp_threads(tmp_path):
+    """tools/abi_latency.cpp: 16 std::threads on one context through the C ABI itself.  The calls overlap (own stream, own
+    workspace, no context-wide lock): the concurrent call rate must be several times the single caller's."""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_latency")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tools", "abi_latency.cpp"), "-L", os.path.join(root, "rustsasa_b200"), "-lsasa_b200",
+                    "-Wl,-rpath," + os.path.join(root, "rustsasa_b200"), "-o", exe], check=True)
+    out = subprocess.run([exe, "2622", "16", "300"], check=True, stdout=subprocess.PIPE, text=True).stdout
+    r = json.loads(out.strip().splitlines()[-1])
+    print(r)
+    assert r["errors"] == 0
+    assert r["speedup"] >= 5.0, r
+
+
+def test_single_structure_levels_through_run_batch(eng, oracle, golden):
+    """sasa_b200_run_batch with S = 1 (what SASAOptions::process does for one file) takes the one-structure path with its
+    level sums: residue / protein outputs equal the oracle's, for a small and a large structure, with and without ids."""
+    import ctypes as C
+    from rustsasa_b200 import _lib
+    L = eng._L
+    for name in ("example.cif", "1jz8"):
+        s = golden.structure(name)
+        x = np.ascontiguousarray(s["xyzr"], np.float32)
+        n, g = x.shape[0], len(s["seg_be"])
+        off = np.array([0, n], np.uint64)
+        soff = np.array([0, g], np.uint64)
+        seg_be = np.ascontiguousarray(s["seg_be"], np.uint32)
+        pol = np.ascontiguousarray(s["polar"], np.uint8)
+        counts = np.zeros(n, np.uint32); atom = np.zeros(n, np.float32); seg = np.zeros(g, np.float32); prot = np.zeros(3, np.float32)
+        outs = _lib.Outputs(counts.ctypes.data, atom.ctypes.data, seg.ctypes.data, prot.ctypes.data)
+        prm = _lib.Params(PROBE, 100, 8, -1, 0)
+        st = _lib.Stats()
+        for cls in (None, np.arange(n, dtype=np.uint32)):
+            rc = L.sasa_b200_run_batch(eng._h, x.ctypes.data, None if cls is None else cls.ctypes.data, off.ctypes.data, 1,
+                                       seg_be.ctypes.data, soff.ctypes.data, pol.ctypes.data, C.byref(prm), C.byref(outs), C.byref(st))
+            assert rc == 0, L.sasa_b200_last_error(eng._h)
+            o = oracle.calculate_sasa_internal(x, PROBE, 100)
+            assert np.array_equal(counts, o["counts"]) and np.array_equal(atom, o["sasa"])
+            assert np.array_equal(seg, oracle.segment_sums(o["sasa"], s["seg_be"]))
+            want = oracle.protein_totals(o["sasa"], s["seg_be"], s["polar"])
+            assert np.array_equal(prot, want) if n <= 16384 else close_enough(prot, want)
+            assert st.gpu_launches <= 8
