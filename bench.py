@@ -32,7 +32,9 @@ N_POINTS = 100
 PROBE = 1.4
 FLOP_PER_TEST = 6.0       # 1 FMUL + 2 FFMA + 1 FSETP per point-neighbour test
 FLOP_PER_PAIR = 20.0      # per-pair setup (3 sub, vmag, limit incl. the division)
-BYTES_PER_ATOM = 24.5     # 16 B float4 in + 4 B count + 4 B SASA + ~0.5 B residue sum
+# algorithmic bytes per atom of THIS run (SURVEY.md 8d lists 16 B float4 in + 4 B count + 4 B SASA + ~0.5 B residue sum; a
+# ResidueLevel run writes neither the counts nor the per-atom areas): 16 B in + 4 B per residue sum out
+BYTES_IN_PER_ATOM = 16.0
 
 
 def env_int(name, default):
@@ -164,7 +166,8 @@ def cpu_sample(data, seconds_target=15.0, threads=0):
 
 
 def run_reference(args, rank):
-    """CPU arm: rank 0 alone works; the other ranks exit 0."""
+    """CPU arm: rank 0 alone works; the other ranks exit 0.  Every step is the WHOLE batch of the GPU arm's configuration
+    (3 s on 16 cores), the oracle's -O3 build with the reference's directory-mode threading on all host cores."""
     if rank != 0:
         return
     from rustsasa_b200 import workloads as W
@@ -172,32 +175,286 @@ def run_reference(args, rank):
     from oracle import load
     fast = load(fast=True)
     cores = host_threads()
-    # bounded sample per step so that (warmup + steps) stays within a few minutes
-    info, _, (n, a1, g1) = cpu_sample(data, seconds_target=max(3.0, 60.0 / max(1, args.steps + args.warmup)))
+    S, N, G = data.n_structures, data.n_atoms, int(data.seg_be.shape[0])
     times = []
+    out = None
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        fast.run_batch(data.xyzr[:a1], data.struct_off[:n + 1], PROBE, N_POINTS, 8, cores,
-                       seg_be=data.seg_be[:g1], struct_seg_off=data.struct_seg_off[:n + 1], want_counts=False)
+        out = fast.run_batch(data.xyzr, data.struct_off, PROBE, N_POINTS, 8, cores, seg_be=data.seg_be,
+                             struct_seg_off=data.struct_seg_off, want_counts=(i == 0))
         if i >= args.warmup:
             times.append(time.perf_counter() - t0)
     dt = float(np.mean(times))
-    v = a1 / dt
-    info.update(value=v)
+    v = N / dt
+    info = dict(value=v, unit=UNIT, cores=cores, kind="port",
+                sample=f"all {S} structures ({N} atoms) per step, {dt:.1f} s, one structure per task on {cores} threads "
+                       f"(C restatement of RustSASA's CPU path, -O3 -march=native; the Rust crate cannot be built here)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "level": "residue", "n_points": N_POINTS, "probe": PROBE,
-                   "radii": "ProtOr", "sample_structures": n, "sample_atoms": a1},
+        "config": bench_config(args, data, args.gpus),
         "cpu_baseline": info,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+def bench_config(args, data, world):
+    """The same dict in both arms (the driver compares them)."""
+    return {"workload": workload_name(args), "level": "residue", "n_points": N_POINTS, "probe": PROBE, "radii": "ProtOr",
+            "structures": data.n_structures, "atoms": data.n_atoms, "residues": int(data.seg_be.shape[0]),
+            "parallelism": f"structures sharded over {world} GPU(s), no collective; every rank its own seeded batch of this shape",
+            "l2": "inputs (16 B x atoms = %.0f MB per step) exceed the 126 MB L2; no flush needed" % (data.n_atoms * 16 / 1e6)}
+
+
 def workload_name(args):
     return (f"cfg2 synthetic AlphaFold-like proteome batch: {args.structures} structures of ~2.4k atoms "
             f"(fragments of the reference's tests/data coordinate sets, rigid transform + 0.05 A jitter), seed 20261017")
+
+
+def bind_rank_to_cores(local_rank, world):
+    """N > 1: give every rank its own slice of the host cores near its GPU (NVML's ideal-CPU mask), before any pinned buffer is
+    allocated, so that eight host pipelines neither migrate nor share cores (e2e efficiency 0.875 at 8 GPUs with
+    unbound ranks).  Returns a short description for the JSON line."""
+    if world <= 1:
+        return None
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        near = allowed
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed) // 64) + 1)
+            mask = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+            near = [c for c in allowed if c in set(mask)] or allowed
+        except Exception:
+            pass
+        per = max(1, len(near) // world)
+        mine = near[(local_rank * per) % len(near):][:per] or near
+        os.sched_setaffinity(0, mine)
+        return f"rank bound to {len(mine)} cores {mine[0]}-{mine[-1]}"
+    except Exception as e:   # affinity is an optimisation, never a failure
+        return f"unbound ({e})"
+
+
+def sha_counts(counts):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(counts, dtype="<u4").tobytes()).hexdigest()
+
+
+def secondary_configs(args, eng, rank, world, local_rank, weak_seg_rank0):
+    """BASELINE.json configs 2 (strong scaling), 3, 4 and 5 measured after the headline legs; every entry carries its own
+    parity flag.  Times are CUDA events / host clocks bracketed by barriers, max over ranks.  Returned on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from rustsasa_b200 import workloads as W
+    from rustsasa_b200.engine import BatchResult
+    from rustsasa_b200.shard import partition_structures, run_atom_range, take_shard
+    out = {}
+    reps = max(3, min(args.steps, 10))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def allr(flag):
+        t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t[0] > 0.5)
+
+    def timed_events(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return maxr(e0.elapsed_time(e1) / n)
+
+    def timed_wall(fn, n):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n
+        barrier()
+        return maxr(dt * 1e3)
+
+    with open(os.path.join(ROOT, "tests", "golden", "cfg_hashes.json")) as fh:
+        golden = json.load(fh)
+
+    # ---- cfg2, STRONG scaling: the one seeded batch of the N = 1 run cut into contiguous cost-balanced shards -------------
+    try:
+        d = W.proteome_batch(args.structures, seed=W.SEED)
+        bounds = partition_structures(d.struct_off, world, N_POINTS)
+        sh = take_shard(bounds, rank, d.xyzr, d.struct_off, d.seg_be, d.struct_seg_off, d.seg_polar)
+        b = eng.batch(sh.struct_off, sh.seg_be, sh.struct_seg_off, sh.seg_polar)
+        na, ng = sh.a1 - sh.a0, sh.g1 - sh.g0
+        d_x = torch.from_numpy(np.ascontiguousarray(sh.xyzr)).cuda()
+        d_seg = torch.zeros(max(ng, 1), dtype=torch.float32, device="cuda")
+        h_x = eng.pinned_empty((na, 4), np.float32)
+        h_x[...] = sh.xyzr
+        res = BatchResult(seg_sasa=eng.pinned_empty(max(ng, 1), np.float32))
+        run_d = lambda: b.run_device(d_x, seg_sasa=d_seg, probe_radius=PROBE, n_points=N_POINTS)   # noqa: E731
+        run_h = lambda: b.run_host(h_x, probe_radius=PROBE, n_points=N_POINTS, result=res)          # noqa: E731
+        for _ in range(2):
+            run_d()
+            run_h()
+        dev_ms = timed_events(run_d, reps)
+        e2e_ms = timed_wall(run_h, reps)
+        # results gathered on rank 0 (they sit in host memory; sizes are known from the partition)
+        G = int(d.seg_be.shape[0])
+        gathered = None
+        t_g = time.perf_counter()
+        if world > 1:
+            sizes = [int(d.struct_seg_off[bounds[r + 1]] - d.struct_seg_off[bounds[r]]) for r in range(world)]
+            pad = max(sizes)
+            mine = torch.zeros(pad, dtype=torch.float32, device="cuda")
+            mine[:ng] = torch.from_numpy(np.asarray(res.seg_sasa)[:ng].copy()).cuda()
+            allb = torch.empty(pad * world, dtype=torch.float32, device="cuda")
+            dist.all_gather_into_tensor(allb, mine)
+            if rank == 0:
+                a = allb.cpu().numpy()
+                gathered = np.concatenate([a[r * pad: r * pad + sizes[r]] for r in range(world)])
+        else:
+            gathered = np.asarray(res.seg_sasa)[:ng].copy()
+        gather_ms = (time.perf_counter() - t_g) * 1e3
+        ok = True
+        if rank == 0:
+            ok = gathered.shape[0] == G and (weak_seg_rank0 is None or bool(np.array_equal(gathered, weak_seg_rank0)))
+        out["cfg2_strong"] = {
+            "workload": "the seeded 4,400-structure batch of the N = 1 run, cut by shard.partition_structures into contiguous "
+                        "cost-balanced shards, one per GPU; no data-path collective, residue sums gathered on rank 0",
+            "scaling": "strong", "structures": d.n_structures, "atoms": d.n_atoms, "value": d.n_atoms / (dev_ms * 1e-3),
+            "ms_per_step": dev_ms, "e2e": {"value": d.n_atoms / (e2e_ms * 1e-3), "ms_per_step": e2e_ms},
+            "gather_ms": gather_ms, "unit": UNIT,
+            "parity": allr(ok), "parity_against": "bit-identical to the single-GPU residue sums of the same batch",
+            "limiter": "per-GPU work shrinks to 1/N of a 6.4 ms step while launch ramp-up, the largest-first tail of one launch and "
+                       "the host call's fixed cost (~0.15 ms) stay"}
+        b.close()
+        del d_x, d_seg, h_x, res, d
+    except Exception as e:   # never lose the headline line to a secondary measurement
+        out["cfg2_strong"] = {"error": repr(e)}
+
+    # ---- cfg3: MD trajectory, ProteinLevel, frames sharded over the ranks ---------------------------------------------------
+    try:
+        F_all = 10000
+        md = W.md_trajectory(n_frames=F_all, n_atoms=5000)
+        NA = md.xyz.shape[1]
+        f0, f1 = F_all * rank // world, F_all * (rank + 1) // world
+        F = f1 - f0
+        G = len(md.seg_be)
+        off = np.arange(F + 1, dtype=np.uint64) * NA
+        b = eng.batch(off, np.tile(md.seg_be, (F, 1)), np.arange(F + 1, dtype=np.uint64) * G, np.tile(md.seg_polar, F))
+        h_xyz = eng.pinned_empty((F * NA, 3), np.float32)
+        h_xyz[...] = md.xyz[f0:f1].reshape(-1, 3)
+        res = BatchResult(protein=eng.pinned_empty((F, 3), np.float32))
+        run_h = lambda: b.run_frames_host(h_xyz, md.radii, want=("protein",), result=res)   # noqa: E731
+        run_h()
+        e2e_ms = timed_wall(run_h, 3)
+        d_xyzr = torch.from_numpy(np.concatenate([md.xyz[f0:f1].reshape(-1, 3), np.tile(md.radii, F)[:, None]], axis=1).astype(np.float32)).cuda()
+        d_prot = torch.zeros((F, 3), dtype=torch.float32, device="cuda")
+        run_d = lambda: b.run_device(d_xyzr, protein=d_prot)   # noqa: E731
+        run_d()
+        dev_ms = timed_events(run_d, 3)
+        from oracle import load
+        orc = load(fast=True)
+        m = min(F, 4)
+        ok = True
+        for f in range(m):
+            xyzr = np.concatenate([md.xyz[f0 + f], md.radii[:, None]], axis=1).astype(np.float32)
+            o = orc.calculate_sasa_internal(xyzr, PROBE, N_POINTS, threads=-1)
+            ok = ok and bool(np.array_equal(np.asarray(res.protein)[f], orc.protein_totals(o["sasa"], md.seg_be, md.seg_polar)))
+        ok = ok and bool(np.array_equal(np.asarray(res.protein), d_prot.cpu().numpy()))
+        out["cfg3_md_frames"] = {
+            "workload": f"{F_all} frames x {NA} atoms, ProteinLevel, 100 points, frames sharded over {world} GPU(s); 12 B/atom/frame "
+                        "on the wire, radii sent once", "scaling": "strong", "atoms": F_all * NA,
+            "value": F_all * NA / (dev_ms * 1e-3), "ms_per_step": dev_ms,
+            "e2e": {"value": F_all * NA / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "frames_per_s": F_all / (e2e_ms * 1e-3),
+                    "h2d_bytes_per_step": F_all * NA * 12, "d2h_bytes_per_step": F_all * 12},
+            "unit": UNIT, "parity": allr(ok),
+            "parity_against": f"oracle protein totals of the first {m} frames of every rank, bit-identical; host leg == device leg"}
+        b.close()
+        del d_xyzr, d_prot, h_xyz, res, md
+    except Exception as e:
+        out["cfg3_md_frames"] = {"error": repr(e)}
+
+    # ---- cfg4: one 150k-atom assembly, AtomLevel, 100 points, single GPU (every rank runs it; rank 0 reports) ------------
+    try:
+        a = W.large_assembly(150000)
+        b = eng.batch(a.struct_off)
+        NA = a.n_atoms
+        h = eng.pinned_empty((NA, 4), np.float32)
+        h[...] = a.xyzr
+        res = BatchResult(atom_sasa=eng.pinned_empty(NA, np.float32), counts=eng.pinned_empty(NA, np.uint32))
+        run_h = lambda: b.run_host(h, n_points=100, want=("counts", "atom"), result=res)   # noqa: E731
+        d_x = torch.from_numpy(a.xyzr).cuda()
+        d_atom = torch.zeros(NA, dtype=torch.float32, device="cuda")
+        run_d = lambda: b.run_device(d_x, n_points=100, atom_sasa=d_atom)   # noqa: E731
+        for _ in range(3):
+            run_h()
+            run_d()
+        e2e_ms = timed_wall(run_h, 10)
+        dev_ms = timed_events(run_d, 10)
+        launches = b.sync()["gpu_launches"]
+        g = golden["cfg4"]
+        ok = NA == g["atoms"] and sha_counts(np.asarray(res.counts)) == g["sha256_counts"]
+        out["cfg4_assembly"] = {"workload": f"one {NA}-atom globule, AtomLevel, 100 points, one GPU", "atoms": NA,
+                                "value": NA / (dev_ms * 1e-3), "ms_per_step": dev_ms, "launches_per_step": int(launches),
+                                "e2e": {"value": NA / (e2e_ms * 1e-3), "ms_per_step": e2e_ms}, "unit": UNIT, "parity": allr(ok),
+                                "parity_against": "sha256 of the oracle's per-atom counts (tests/golden/cfg_hashes.json), exact"}
+        b.close()
+        del d_x, d_atom, h, res, a
+    except Exception as e:
+        out["cfg4_assembly"] = {"error": repr(e)}
+
+    # ---- cfg5: 1M-atom capsid, 960 points, atom ranges split over the ranks + one all-reduce ---------------------------------
+    try:
+        a = W.capsid_shell(1000000)
+        b = eng.batch(a.struct_off)
+        NA = a.n_atoms
+        d_x = torch.from_numpy(a.xyzr).cuda()
+        counts = torch.empty(NA, dtype=torch.int32, device="cuda")
+        atom = torch.empty(NA, dtype=torch.float32, device="cuda")
+
+        def kernels_only():
+            b.run_atom_range_device(d_x, rank, world, n_points=960, counts=counts, atom_sasa=atom)
+
+        def step():
+            run_atom_range(lambda r, w: (kernels_only(), (counts, atom))[1], rank, world)
+        for _ in range(3):
+            step()
+        k_ms = timed_events(kernels_only, 5)
+        dev_ms = timed_events(step, 5)
+        wall_ms = timed_wall(step, 5)
+        step()
+        torch.cuda.synchronize()
+        g = golden["cfg5"]
+        got = counts.cpu().numpy().view(np.uint32)
+        ok = NA == g["atoms"] and int(got.astype(np.int64).sum()) == g["sum_counts"] and sha_counts(got) == g["sha256_counts"]
+        out["cfg5_capsid"] = {
+            "workload": f"one {NA}-atom capsid shell, AtomLevel, 960 points; every rank builds the whole cell list and evaluates its "
+                        f"interleaved share of the cell-sorted atoms; per-rank count / area vectors summed by ncclAllReduce ({world} GPU(s))",
+            "scaling": "strong", "atoms": NA, "value": NA / (dev_ms * 1e-3), "ms_per_step": dev_ms,
+            "kernels_only": {"value": NA / (k_ms * 1e-3), "ms_per_step": k_ms},
+            "wall": {"value": NA / (wall_ms * 1e-3), "ms_per_step": wall_ms}, "unit": UNIT, "parity": allr(ok),
+            "parity_against": "sha256 + sum of the oracle's per-atom counts at full size (tests/golden/cfg_hashes.json), exact",
+            "sum_counts": int(got.astype(np.int64).sum())}
+        b.close()
+    except Exception as e:
+        out["cfg5_capsid"] = {"error": repr(e)}
+    return out
 
 
 def main():
@@ -208,6 +465,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--structures", type=int, default=4400)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2-strong / cfg3 / cfg4 / cfg5 block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -218,6 +476,7 @@ def main():
         run_reference(args, rank)
         return
 
+    binding = bind_rank_to_cores(local_rank, world)
     import torch
     import torch.distributed as dist
     from rustsasa_b200 import Engine
@@ -300,6 +559,14 @@ def main():
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     atoms_all = float(tot[0])
 
+    weak_seg = np.asarray(h_res.seg_sasa).copy() if rank == 0 else None
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    secondary = None
+    if not args.no_secondary:
+        # free the headline buffers first (the secondary configurations bring their own)
+        del d_xyzr, d_seg
+        secondary = secondary_configs(args, eng, rank, world, local_rank, weak_seg)
+
     if rank == 0:
         value = atoms_all * args.steps / (dev_ms_max * 1e-3)
         e2e = atoms_all * args.steps / (e2e_ms_max * 1e-3)
@@ -310,10 +577,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "level": "residue", "n_points": N_POINTS, "probe": PROBE,
-                       "radii": "ProtOr", "structures_per_gpu": data.n_structures, "atoms_per_gpu": N,
-                       "residues_per_gpu": G, "parallelism": f"structures sharded over {world} GPU(s), no collective",
-                       "l2": "inputs (16 B x atoms = %.0f MB per step) exceed the 126 MB L2; no flush needed" % (N * 16 / 1e6)},
+            "config": bench_config(args, data, world),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(N * 16), "d2h_bytes_per_step": int(G * 4),
                     "ms_per_step": e2e_ms_max / args.steps, "timing": "host wall clock around the synchronous C-ABI call"},
             "gpu_launches": int(launches_per_step) * args.steps,
@@ -324,31 +588,37 @@ def main():
                           "streamed_atoms": stats_dev["streamed_atoms"], "launches_per_step": int(launches_per_step),
                           "e2e_device_span_ms": stats_e2e["kernel_ms"]},
         }
+        if binding:
+            out["host_binding"] = binding
         cpu = None
         if not args.no_cpu and world == 1:   # the CPU leg is an N = 1 measurement (rank 0 alone would stall the other ranks)
             cpu, cpu_out, (n, a1, g1) = cpu_sample(data)
             out["cpu_baseline"] = cpu
-            out["parity_on_cpu_sample"] = bool(np.array_equal(cpu_out["seg"], np.asarray(h_res.seg_sasa)[:g1]))
+            out["parity_on_cpu_sample"] = bool(np.array_equal(cpu_out["seg"], weak_seg[:g1]))
         # without the CPU leg: the oracle's figure for this same seeded batch from the committed N = 1 run (profiles/r01h_bench.json)
         k_mean = cpu["k_mean"] if cpu else 43.354429297893255
         flops_per_atom = FLOP_PER_TEST * N_POINTS * k_mean + FLOP_PER_PAIR * k_mean
         per_gpu_step_s = dev_ms_max * 1e-3 / args.steps
         traffic, traffic_info = ncu_traffic(args.structures)
         achieved = N * flops_per_atom / per_gpu_step_s / 1e12
+        alg_bytes = N * BYTES_IN_PER_ATOM + G * 4.0    # what THIS run reads and writes: float4 atoms in, residue sums out
         out["roofline"] = {
             "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
             "traffic": traffic,
             "traffic_unit": "DRAM bytes per step (dram__bytes_read.sum + dram__bytes_write.sum over the step's launches)",
             "traffic_source": (traffic_info or {}).get("source"),
-            "algorithmic_bytes_per_step": N * BYTES_PER_ATOM,
+            "algorithmic_bytes_per_step": alg_bytes,
             "kernel": "sasa_tight_kernel (fused per-structure kernel; all launches of a step)",
             "note": ("FP32 CUDA-core compare roofline (SURVEY.md 8d): algorithmic flops = atoms x (6 x n_points + 20) x k_mean, "
                      f"k_mean = {k_mean:.2f} reference-definition neighbours/atom measured by the oracle on a sample; "
                      f"peak = SMs x 128 x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']}); early exit may legitimately push frac past "
                      "what the executed-instruction count implies"),
-            "hbm": {"achieved": N * BYTES_PER_ATOM / per_gpu_step_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": N * BYTES_PER_ATOM / per_gpu_step_s / 1e9 / pk["hbm_gbs"], "bytes_per_atom": BYTES_PER_ATOM},
+            "hbm": {"achieved": alg_bytes / per_gpu_step_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": alg_bytes / per_gpu_step_s / 1e9 / pk["hbm_gbs"], "bytes_per_atom": alg_bytes / N,
+                    "note": "16 B float4 per atom in + 4 B per residue sum out (a ResidueLevel run writes no per-atom output)"},
         }
+        if secondary is not None:
+            out["secondary"] = secondary
         print(json.dumps(out))
     batch.close()
     eng.close()

@@ -69,25 +69,40 @@ def main():
         print(f"atom-range split over {world} GPUs + all-reduce: parity OK ({a.n_atoms} atoms, 960 points)", flush=True)
     b.close()
 
-    # (3) the same at full cfg5 size (1 M atoms; 100 points keep it quick): slices are cut at cell boundaries, so the
-    # per-rank partitions agree although the order of atoms inside a cell differs from GPU to GPU
+    # (3) BASELINE cfg5 at full size: 1 M atoms x 960 points, atom ranges split over all ranks, against the oracle's
+    # fingerprint (tests/golden/cfg_hashes.json, written by tools/make_cfg_hashes.py) and the single-GPU run.  Work blocks are
+    # cut at cell boundaries, so the per-rank partitions agree although the order of atoms inside a cell differs per GPU.
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "cfg_hashes.json")))["cfg5"]
     a = W.capsid_shell(1000000)
+    assert a.n_atoms == gold["atoms"]
     b = eng.batch(a.struct_off)
     d_xyzr = torch.from_numpy(a.xyzr).cuda()
 
     def compute_range_big(r, w):
         counts = torch.empty(a.n_atoms, dtype=torch.int32, device="cuda")
         atom = torch.empty(a.n_atoms, dtype=torch.float32, device="cuda")
-        b.run_atom_range_device(d_xyzr, r, w, counts=counts, atom_sasa=atom)
+        b.run_atom_range_device(d_xyzr, r, w, n_points=960, counts=counts, atom_sasa=atom)
         return counts, atom
+    single = b.run_host(a.xyzr, n_points=960, want=("counts", "atom"))
+    assert hashlib.sha256(np.ascontiguousarray(single.counts, dtype="<u4").tobytes()).hexdigest() == gold["sha256_counts"]
+    owned = []
     for _ in range(3):
         counts, atom = run_atom_range(compute_range_big)
         torch.cuda.synchronize()
-        single = b.run_host(a.xyzr, want=("counts", "atom"))
         assert np.array_equal(counts.cpu().numpy().view(np.uint32), single.counts)
         assert np.array_equal(atom.cpu().numpy(), single.atom_sasa)
+    # balance of the interleaved ownership: atoms evaluated by this rank
+    mine, _ = compute_range_big(rank, world)
+    part = b.run_atom_range_host(a.xyzr, rank, world, n_points=960)
+    n_mine = torch.tensor([float(((part.counts != 0) | (part.atom_sasa != 0)).sum())], device="cuda")
+    lo, hi = n_mine.clone(), n_mine.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"atom-range split of {a.n_atoms} atoms over {world} GPUs: equals the single-GPU result (3 runs)", flush=True)
+        print(f"atom-range split of {a.n_atoms} atoms x 960 points over {world} GPUs: equals the oracle fingerprint and the single-GPU "
+              f"result (3 runs); exposed atoms per rank {int(lo)}..{int(hi)}", flush=True)
     b.close()
     eng.close()
     dist.barrier()

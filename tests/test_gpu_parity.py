@@ -659,3 +659,28 @@ def test_single_structure_levels_through_run_batch(eng, oracle, golden):
             want = oracle.protein_totals(o["sasa"], s["seg_be"], s["polar"])
             assert np.array_equal(prot, want) if n <= 16384 else close_enough(prot, want)
             assert st.gpu_launches <= 8
+
+
+def test_full_size_configs_match_oracle_fingerprints(eng):
+    """BASELINE cfg4 (150k atoms x 100 points) and cfg5 (1M atoms x 960 points) at FULL size on one GPU: per-atom counts
+    equal the oracle's, through their sha256 + sum stored in tests/golden/cfg_hashes.json (tools/make_cfg_hashes.py runs the
+    CPU oracle; 12 s at 1M x 960).  Both the whole-structure call and the atom-range split (3 ranks, summed) are checked."""
+    import hashlib
+    import json
+    import os
+    from rustsasa_b200 import workloads as W
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = json.load(open(os.path.join(root, "tests", "golden", "cfg_hashes.json")))
+    for key, data in (("cfg4", W.large_assembly(150000)), ("cfg5", W.capsid_shell(1000000))):
+        g = gold[key]
+        assert data.n_atoms == g["atoms"]
+        assert hashlib.sha256(np.ascontiguousarray(data.xyzr).tobytes()).hexdigest() == g["xyzr_sha256"], "workload generator changed"
+        b = eng.batch(data.struct_off)
+        r = b.run_host(data.xyzr, n_points=g["n_points"], want=("counts", "atom"))
+        assert int(r.counts.astype(np.int64).sum()) == g["sum_counts"]
+        assert hashlib.sha256(np.ascontiguousarray(r.counts, dtype="<u4").tobytes()).hexdigest() == g["sha256_counts"]
+        assert r.stats["streamed_atoms"] == 0
+        parts = [b.run_atom_range_host(data.xyzr, k, 3, n_points=g["n_points"]) for k in range(3)]
+        assert np.array_equal(parts[0].counts + parts[1].counts + parts[2].counts, r.counts)
+        assert np.array_equal(parts[0].atom_sasa + parts[1].atom_sasa + parts[2].atom_sasa, r.atom_sasa)
+        b.close()
