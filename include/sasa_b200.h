@@ -108,6 +108,8 @@ typedef struct sasa_b200_stats {
 
 /* ---- context ---------------------------------------------------------------------- */
 SASA_B200_API int sasa_b200_abi_version(void);
+/* Number of CUDA devices this process can use (0 and SASA_B200_ERR_CUDA without a driver / device). */
+SASA_B200_API int sasa_b200_device_count(int *out_count);
 /* device < 0 selects the current CUDA device. */
 SASA_B200_API int sasa_b200_create(int device, sasa_b200_ctx **out_ctx);
 SASA_B200_API void sasa_b200_destroy(sasa_b200_ctx *ctx);

@@ -209,7 +209,10 @@ Packed build_atoms_and_mapping(const pdb::PDB &pdb, LevelKind level, const Optio
 using ProcessOutcome = std::variant<SASAResult, SASACalcError>;
 std::vector<ProcessOutcome> process_many(const std::vector<const pdb::PDB *> &pdbs, LevelKind level, const OptionValues &opt);
 // Same, from already extracted atoms (what a caller with its own parser uses).
-std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &packed, LevelKind level, const OptionValues &opt);
+// device < 0: the process's default engine device (set_device / SASA_B200_DEVICE / 0).  Calls on different devices run
+// concurrently (one engine context, one staging buffer each): directory mode deals its tiles round-robin over the devices.
+std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &packed, LevelKind level, const OptionValues &opt,
+                                           int device = -1);
 
 template <class Level>
 class SASAOptions {
@@ -253,7 +256,9 @@ std::string sasa_result_to_xml(const SASAResult &result);    // quick_xml::se::t
 void sasa_result_to_protein_object(pdb::PDB &original_pdb, const SASAResult &result);
 
 // Optional: create the engine context and the per-n_points tables now (e.g. on a helper thread while files are parsed).
-void warm_up(const OptionValues &opt);
+void warm_up(const OptionValues &opt, int device = -1);
+// CUDA devices visible to this process (0 when there is none).
+int device_count();
 
 // Engine selection for this process: CUDA device ordinal used by every call above (default: SASA_B200_DEVICE or 0).
 void set_device(int device);

@@ -24,6 +24,7 @@ EXPORTS = [
     "sasa_b200_batch_run_frames_host", "sasa_b200_run_batch", "sasa_b200_batch_run_atom_range_device",
     "sasa_b200_batch_run_atom_range_host", "sasa_b200_batch_reduce_device",
     "sasa_b200_batch_submit_host", "sasa_b200_batch_submit_frames_host", "sasa_b200_job_wait",
+    "sasa_b200_device_count",
 ]
 
 
@@ -62,6 +63,7 @@ def load() -> C.CDLL:
     vp, sz = C.c_void_p, C.c_size_t
     L.sasa_b200_abi_version.restype = C.c_int
     L.sasa_b200_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.sasa_b200_device_count.argtypes = [C.POINTER(C.c_int)]
     L.sasa_b200_destroy.argtypes = [vp]
     L.sasa_b200_destroy.restype = None
     L.sasa_b200_last_error.argtypes = [vp]

@@ -149,3 +149,58 @@ HOST_API float sasa_b200_host_get_radius(const char *res, const char *atom) {
     auto r = get_radius(res, atom, nullptr);
     return r ? *r : -1.0f;
 }
+
+// ---- the reader's hierarchy, flattened for the reader tests (pdbtbx/tests/*.rs restated in tests/test_reader_pins.py) ----
+// Every atom of the file in hierarchy order (models -> chains -> residues -> conformers -> atoms, like PDB::atoms()).
+namespace {
+struct FlatAtoms {
+    std::vector<double> xyzob;          // x, y, z, occupancy, b per atom
+    std::vector<long long> ints;        // serial, residue serial, model index, model serial, hetero, is_hydrogen, conformer index, residue index per atom
+    std::string text;                   // per atom "chain|icode|altloc|resname|name|element\n"
+    size_t models = 0, chains = 0, residues = 0, conformers = 0;
+};
+}  // namespace
+
+HOST_API void *sasa_b200_host_flatten(const char *path, char *err, size_t errlen) {
+    try {
+        const pdb::PDB st = pdb::open(path);
+        auto *f = new FlatAtoms();
+        f->models = st.models.size();
+        long long mi = 0, ri = 0;
+        for (const auto &m : st.models) {
+            f->chains += m.chains.size();
+            for (const auto &c : m.chains)
+                for (const auto &r : c.residues) {
+                    ++f->residues;
+                    long long ci = 0;
+                    for (const auto &cf : r.conformers) {
+                        ++f->conformers;
+                        for (const auto &a : cf.atoms) {
+                            f->xyzob.insert(f->xyzob.end(), {a.x, a.y, a.z, a.occupancy, a.b_factor});
+                            f->ints.insert(f->ints.end(), {(long long)a.serial, (long long)r.serial, mi, (long long)m.serial, (long long)a.hetero,
+                                                           (long long)(a.element == "H"), ci, ri});
+                            f->text += c.id + "|" + r.icode + "|" + cf.altloc + "|" + cf.name + "|" + a.name + "|" + a.element + "\n";
+                        }
+                        ++ci;
+                    }
+                    ++ri;
+                }
+            ++mi;
+        }
+        return f;
+    } catch (const std::exception &e) {
+        put_error(err, errlen, std::string("IO: ") + e.what());
+    }
+    return nullptr;
+}
+HOST_API void sasa_b200_host_flat_sizes(const void *h, size_t *out /* atoms, models, chains, residues, conformers, text bytes */) {
+    const FlatAtoms &f = *static_cast<const FlatAtoms *>(h);
+    out[0] = f.ints.size() / 8; out[1] = f.models; out[2] = f.chains; out[3] = f.residues; out[4] = f.conformers; out[5] = f.text.size();
+}
+HOST_API void sasa_b200_host_flat_copy(const void *h, double *xyzob, long long *ints, char *text) {
+    const FlatAtoms &f = *static_cast<const FlatAtoms *>(h);
+    if (xyzob) std::memcpy(xyzob, f.xyzob.data(), f.xyzob.size() * sizeof(double));
+    if (ints) std::memcpy(ints, f.ints.data(), f.ints.size() * sizeof(long long));
+    if (text) std::memcpy(text, f.text.data(), f.text.size());
+}
+HOST_API void sasa_b200_host_flat_free(void *h) { delete static_cast<FlatAtoms *>(h); }

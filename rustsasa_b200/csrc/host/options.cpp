@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -46,24 +47,40 @@ std::uint64_t atom_id_hash(const std::string &altloc, std::size_t serial) {
     return h;
 }
 
+// One engine context and one grow-only pinned staging buffer per device, created on first use.
+struct DeviceState {
+    sasa_b200_ctx *ctx = nullptr;
+    std::mutex pin_mu;   // one tile at a time owns the staging buffer of a device
+    void *pin = nullptr;
+    size_t pin_bytes = 0;
+};
 int g_device = -1;
 std::mutex g_ctx_mu;
-sasa_b200_ctx *g_ctx = nullptr;
+std::map<int, std::unique_ptr<DeviceState>> g_devices;
 
-sasa_b200_ctx *context() {
-    std::lock_guard<std::mutex> lk(g_ctx_mu);
-    if (g_ctx) return g_ctx;
-    int device = g_device;
-    if (device < 0) {
-        const char *e = std::getenv("SASA_B200_DEVICE");
-        device = e ? std::atoi(e) : 0;
+DeviceState &device_state(int device) {
+    DeviceState *st = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        if (device < 0) device = g_device;
+        if (device < 0) {
+            const char *e = std::getenv("SASA_B200_DEVICE");
+            device = e ? std::atoi(e) : 0;
+        }
+        auto &slot = g_devices[device];
+        if (!slot) slot = std::make_unique<DeviceState>();
+        st = slot.get();
     }
-    if (sasa_b200_create(device, &g_ctx) != SASA_B200_OK) {
-        g_ctx = nullptr;
+    // context creation (hundreds of milliseconds) happens outside the registry lock: devices come up in parallel
+    std::lock_guard<std::mutex> lk(st->pin_mu);
+    if (!st->ctx && sasa_b200_create(device, &st->ctx) != SASA_B200_OK) {
+        st->ctx = nullptr;
         throw SASACalcError(SASACalcError::Kind::Device, std::string("sasa_b200_create failed: ") + sasa_b200_last_error(nullptr));
     }
-    return g_ctx;
+    return *st;
 }
+
+sasa_b200_ctx *context(int device = -1) { return device_state(device).ctx; }
 
 [[noreturn]] void throw_device(sasa_b200_ctx *ctx, const char *what) {
     throw SASACalcError(SASACalcError::Kind::Device, std::string(what) + ": " + sasa_b200_last_error(ctx));
@@ -103,31 +120,33 @@ void parallel_for(size_t n, F &&f) {
     for (auto &t : pool) t.join();
 }
 
-// Grow-only pinned staging buffer of this process (a cudaHostAlloc per tile cost tens of milliseconds).
-std::mutex g_pin_mu;
-void *g_pin = nullptr;
-size_t g_pin_bytes = 0;
-void *pinned_reserve(size_t bytes) {
-    if (bytes <= g_pin_bytes) return g_pin;
-    if (g_pin) sasa_b200_free_pinned(g_pin);
-    g_pin = nullptr;
-    g_pin_bytes = 0;
+// Grow-only pinned staging buffer of a device (a cudaHostAlloc per tile cost tens of milliseconds); st.pin_mu is held.
+void *pinned_reserve(DeviceState &st, size_t bytes) {
+    if (bytes <= st.pin_bytes) return st.pin;
+    if (st.pin) sasa_b200_free_pinned(st.pin);
+    st.pin = nullptr;
+    st.pin_bytes = 0;
     const size_t want = bytes + bytes / 4 + (1 << 20);
-    if (sasa_b200_alloc_pinned(want, &g_pin) != SASA_B200_OK) return nullptr;
-    g_pin_bytes = want;
-    return g_pin;
+    if (sasa_b200_alloc_pinned(want, &st.pin) != SASA_B200_OK) return nullptr;
+    st.pin_bytes = want;
+    return st.pin;
 }
 
 }  // namespace
 
 // Creates the engine context and the tables of this point count ahead of the first real call (CUDA context creation,
 // module load and the cap table are a few hundred milliseconds): the CLI runs this while it parses its first files.
-void warm_up(const OptionValues &opt) {
+int device_count() {
+    int n = 0;
+    return sasa_b200_device_count(&n) == SASA_B200_OK ? n : 0;
+}
+
+void warm_up(const OptionValues &opt, int device) {
     const bool trace = std::getenv("SASA_B200_TRACE") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
-    sasa_b200_ctx *ctx = context();
-    if (trace) std::fprintf(stderr, "[sasa_b200] context created at %.3f s\n", since());
+    sasa_b200_ctx *ctx = context(device);
+    if (trace) std::fprintf(stderr, "[sasa_b200] context of device %d created at %.3f s\n", device, since());
     const float one[4] = {0.0f, 0.0f, 0.0f, 1.5f};
     float out = 0.0f;
     sasa_b200_calculate_sasa_internal(ctx, one, nullptr, 1, opt.probe_radius, opt.n_points, opt.threads, &out, nullptr);
@@ -228,7 +247,8 @@ Packed build_atoms_and_mapping(const pdb::PDB &pdb, LevelKind level, const Optio
 }
 
 // ---- the batched engine call ----------------------------------------------------------------------------------------
-std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &packed, LevelKind level, const OptionValues &opt) {
+std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &packed, LevelKind level, const OptionValues &opt,
+                                           int device) {
     std::vector<ProcessOutcome> results;
     const size_t S = packed.size();
     std::vector<std::uint64_t> struct_off(S + 1, 0), seg_off(S + 1, 0);
@@ -237,7 +257,8 @@ std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &pa
         seg_off[s + 1] = seg_off[s] + packed[s]->seg_polar.size();
     }
     const size_t N = struct_off[S], G = seg_off[S];
-    sasa_b200_ctx *ctx = context();
+    DeviceState &dev = device_state(device);
+    sasa_b200_ctx *ctx = dev.ctx;
     if (S == 1 && N > 0) {
         // One structure (SASAOptions::process, src/options.rs:606-618): the engine's one-structure call runs on a stream and
         // workspace of its own, so callers on many threads overlap (the reference's directory mode, src/main.rs:375).
@@ -271,9 +292,9 @@ std::vector<ProcessOutcome> process_packed(const std::vector<const Packed *> &pa
         return results;
     }
     // pinned staging: the pipelined host entry point overlaps H2D, kernels and D2H across chunks
-    std::lock_guard<std::mutex> pin_lock(g_pin_mu);   // one tile at a time owns the staging buffer
+    std::lock_guard<std::mutex> pin_lock(dev.pin_mu);   // one tile at a time owns the staging buffer of a device
     const size_t in_bytes = N * 16, out_atom = level == LevelKind::Atom ? N * 4 : 0, out_seg = G * 4, out_prot = S * 12;
-    void *pin = pinned_reserve(in_bytes + out_atom + out_seg + out_prot + 64);
+    void *pin = pinned_reserve(dev, in_bytes + out_atom + out_seg + out_prot + 64);
     if (!pin) throw_device(nullptr, "alloc_pinned");
     float *h_xyzr = static_cast<float *>(pin);
     float *h_atom = reinterpret_cast<float *>(static_cast<char *>(pin) + in_bytes);

@@ -555,6 +555,16 @@ int sasa_b200_abi_version(void) { return SASA_B200_ABI_VERSION; }
 
 const char *sasa_b200_last_error(const sasa_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+int sasa_b200_device_count(int *out_count) {
+    if (!out_count) return SASA_B200_ERR_INVALID_ARGUMENT;
+    *out_count = 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return fail(nullptr, SASA_B200_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));
+    *out_count = count;
+    return SASA_B200_OK;
+}
+
 int sasa_b200_create(int device, sasa_b200_ctx **out_ctx) {
     if (!out_ctx) return fail(nullptr, SASA_B200_ERR_INVALID_ARGUMENT, "out_ctx is NULL");
     *out_ctx = nullptr;

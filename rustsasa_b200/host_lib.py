@@ -51,8 +51,44 @@ def load() -> C.CDLL:
         L.sasa_b200_host_serialize_chain_id.restype = C.c_long
         L.sasa_b200_host_get_radius.argtypes = [C.c_char_p, C.c_char_p]
         L.sasa_b200_host_get_radius.restype = C.c_float
+        L.sasa_b200_host_flatten.argtypes = [C.c_char_p, C.c_char_p, sz]
+        L.sasa_b200_host_flatten.restype = vp
+        L.sasa_b200_host_flat_sizes.argtypes = [vp, vp]
+        L.sasa_b200_host_flat_sizes.restype = None
+        L.sasa_b200_host_flat_copy.argtypes = [vp, vp, vp, vp]
+        L.sasa_b200_host_flat_copy.restype = None
+        L.sasa_b200_host_flat_free.argtypes = [vp]
+        L.sasa_b200_host_flat_free.restype = None
         _lib = L
     return _lib
+
+
+def flatten(path: str):
+    """The C++ reader's hierarchy of a file, one row per atom in hierarchy order (all models, all conformers):
+    dict(xyz, occupancy, b_factor, serial, res_serial, model_index, model_serial, hetero, is_h, conformer_index,
+    residue_index, chain, icode, altloc, resname, name, element, n_models, n_chains, n_residues, n_conformers)."""
+    L = load()
+    err = C.create_string_buffer(512)
+    h = L.sasa_b200_host_flatten(path.encode(), err, 512)
+    if not h:
+        raise HostError(err.value.decode())
+    try:
+        sizes = (C.c_size_t * 6)()
+        L.sasa_b200_host_flat_sizes(h, sizes)
+        n = sizes[0]
+        xyzob = np.zeros((n, 5), np.float64)
+        ints = np.zeros((n, 8), np.int64)
+        text = C.create_string_buffer(max(1, sizes[5]))
+        L.sasa_b200_host_flat_copy(h, xyzob.ctypes.data, ints.ctypes.data, text)
+    finally:
+        L.sasa_b200_host_flat_free(h)
+    rows = [r.split("|") for r in text.raw[:sizes[5]].decode().split("\n")[:-1]] if n else []
+    col = lambda k: [r[k] for r in rows]   # noqa: E731
+    return dict(xyz=xyzob[:, :3], occupancy=xyzob[:, 3], b_factor=xyzob[:, 4], serial=ints[:, 0], res_serial=ints[:, 1],
+                model_index=ints[:, 2], model_serial=ints[:, 3], hetero=ints[:, 4].astype(bool), is_h=ints[:, 5].astype(bool),
+                conformer_index=ints[:, 6], residue_index=ints[:, 7], chain=col(0), icode=col(1), altloc=col(2), resname=col(3),
+                name=col(4), element=col(5), n_models=int(sizes[1]), n_chains=int(sizes[2]), n_residues=int(sizes[3]),
+                n_conformers=int(sizes[4]))
 
 
 def pack(path: str, level: str = "residue", include_hydrogens=False, include_hetatms=False, allow_vdw_fallback=False,

@@ -234,8 +234,17 @@ def read_pdb(path: str) -> Structure:
     res_add = 0
     last_serial = -1
     last_res = -1
+    # blank chain IDs take the letter of an 'A'..'Z' cycle advanced by every TER record and never reset
+    # (pdbtbx/src/read/pdb/parser.rs:113-115, :176-180, :511)
+    chain_letter = 0
+    model_no = 0
     with open(path, "r", errors="replace") as fh:
         for line in fh:
+            line = line.rstrip("\r\n")
+            if len(line) <= 6:          # short lines: only TER counts (pdbtbx lexer.rs:87-91)
+                if line[:3] == "TER":
+                    chain_letter = (chain_letter + 1) % 26
+                continue
             rec = line[:6]
             if rec in ("ATOM  ", "HETATM"):
                 line = line.rstrip("\n").ljust(80)
@@ -258,21 +267,28 @@ def read_pdb(path: str) -> Structure:
                     res_add += 10000
                 atom = AtomRec(rec == "HETATM", serial + serial_add, name, x, y, z, occ,
                                _element(line[76:78], name))
-                _add_atom(model, chain_id if chain_id.strip() else "A",
+                _add_atom(model, chain_id if chain_id.strip() else chr(ord("A") + chain_letter),
                           (resseq + res_add, None if icode == " " else icode),
                           (resname, None if alt == " " else alt), atom)
                 last_serial, last_res = serial, resseq
             elif rec == "MODEL ":
+                # closed by the NEXT MODEL record (or MASTER, or the end of the file); ENDMDL is ignored (parser.rs:282-306)
+                model.serial = model_no
                 if model.chains:
                     st.models.append(model)
                 try:
-                    model = Model(int(line[6:].strip() or 0))
+                    model_no = int(line[6:].strip())
                 except ValueError:
-                    model = Model(len(st.models) + 1)
-            elif rec.startswith("ENDMDL"):
+                    model_no = 0
+                model = Model(model_no)
+            elif rec == "MASTER":
+                model.serial = model_no
                 if model.chains:
                     st.models.append(model)
-                model = Model(model.serial + 1)
+                model = Model(model_no)
+            elif rec == "TER   ":
+                chain_letter = (chain_letter + 1) % 26
+    model.serial = model_no
     if model.chains:
         st.models.append(model)
     _reshuffle_conformers(st)

@@ -306,3 +306,13 @@ def test_residue_and_chain_json_shape(host):
     back = json.loads(host.format_values(v, kind="residue"))["Residue"]
     assert [r["serial_number"] for r in back] == list(range(1, 701))
     assert np.array_equal(np.array([r["value"] for r in back], np.float32), v)
+
+
+def test_cli_rejects_malformed_numbers_with_a_usage_error(host):
+    """clap in the reference reports an invalid numeric value and exits with code 2; an uncaught std::invalid_argument
+    (abort) is not acceptable.  No engine call is made, so this runs without a GPU."""
+    import subprocess
+    for bad in (["-n", "abc"], ["-n", "0"], ["-n", "-5"], ["-p", "1.x"], ["-t", "many"], ["--tile", "0"], ["--devices", "x"], ["-n"]):
+        r = subprocess.run([host.CLI_PATH] + bad + ["in", "out"], capture_output=True, text=True)
+        assert r.returncode == 2, (bad, r.returncode, r.stderr[:200])
+        assert "error:" in r.stderr and "Usage:" in r.stderr
