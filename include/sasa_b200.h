@@ -180,6 +180,19 @@ SASA_B200_API int sasa_b200_batch_run_frames_host(sasa_b200_batch *batch, const 
                                     const sasa_b200_params *params, const sasa_b200_outputs *out,
                                     sasa_b200_stats *stats /* nullable */);
 
+/* Indexed-radius form: 13 bytes per atom on the wire instead of 16.  Proteins use a handful of distinct radii (ProtOr,
+ * radii/protor.config, has ten), so the extraction step (build_atoms_and_mapping, src/options.rs:81-116) can emit
+ * coordinates as 3 floats per atom plus ONE BYTE per atom indexing a palette of at most 256 radii.  With eight GPUs pulling
+ * their batches over PCIe at once the host copy is the limiter, and it scales with the bytes.  Same results as the float4
+ * form bit for bit; the fused kernels read this form directly.  xyz: n_atoms * 3 floats; radius_index: n_atoms bytes. */
+SASA_B200_API int sasa_b200_batch_run_indexed_host(sasa_b200_batch *batch, const float *xyz, const uint8_t *radius_index,
+                                     const float *palette, size_t n_palette, const uint32_t *id_class,
+                                     const sasa_b200_params *params, const sasa_b200_outputs *out,
+                                     sasa_b200_stats *stats /* nullable */);
+SASA_B200_API int sasa_b200_batch_submit_indexed_host(sasa_b200_batch *batch, const float *xyz, const uint8_t *radius_index,
+                                        const float *palette, size_t n_palette, const uint32_t *id_class,
+                                        const sasa_b200_params *params, const sasa_b200_outputs *out, sasa_b200_job **out_job);
+
 /* Atom-range split of large structures over several GPUs (BASELINE.json config 5: a 1M-atom capsid at 960 points
  * split across 8 GPUs).  The reference has no counterpart -- its neighbour build is serial and its atom loop is a
  * rayon par_iter inside one process (src/lib.rs:278-290); this is that par_iter cut across devices.  Every rank

@@ -24,7 +24,7 @@ EXPORTS = [
     "sasa_b200_batch_run_frames_host", "sasa_b200_run_batch", "sasa_b200_batch_run_atom_range_device",
     "sasa_b200_batch_run_atom_range_host", "sasa_b200_batch_reduce_device",
     "sasa_b200_batch_submit_host", "sasa_b200_batch_submit_frames_host", "sasa_b200_job_wait",
-    "sasa_b200_device_count",
+    "sasa_b200_device_count", "sasa_b200_batch_run_indexed_host", "sasa_b200_batch_submit_indexed_host",
 ]
 
 
@@ -81,6 +81,8 @@ def load() -> C.CDLL:
     L.sasa_b200_batch_submit_host.argtypes = [vp, vp, vp, C.POINTER(Params), C.POINTER(Outputs), C.POINTER(vp)]
     L.sasa_b200_batch_submit_frames_host.argtypes = [vp, vp, vp, C.POINTER(Params), C.POINTER(Outputs), C.POINTER(vp)]
     L.sasa_b200_job_wait.argtypes = [vp, C.POINTER(Stats)]
+    L.sasa_b200_batch_run_indexed_host.argtypes = [vp, vp, vp, vp, sz, vp, C.POINTER(Params), C.POINTER(Outputs), C.POINTER(Stats)]
+    L.sasa_b200_batch_submit_indexed_host.argtypes = [vp, vp, vp, vp, sz, vp, C.POINTER(Params), C.POINTER(Outputs), C.POINTER(vp)]
     L.sasa_b200_batch_run_frames_host.argtypes = [vp, vp, vp, C.POINTER(Params), C.POINTER(Outputs), C.POINTER(Stats)]
     L.sasa_b200_batch_run_atom_range_device.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, C.c_uint32, vp, vp, vp]
     L.sasa_b200_batch_run_atom_range_host.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, C.c_uint32, vp, vp,

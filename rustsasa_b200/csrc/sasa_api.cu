@@ -865,7 +865,7 @@ static int job_abort(sasa_b200_ctx *ctx, sasa_b200_job *j, int rc) {
 
 static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *xyz3, const float *radii,
                             const uint32_t *id_class, const sasa_b200_params *params, const sasa_b200_outputs *out,
-                            sasa_b200_job **out_job) {
+                            sasa_b200_job **out_job, const uint8_t *ridx = nullptr, size_t n_palette = 0) {
     sasa_b200_ctx *ctx = b->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!out || !out_job) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "out / out_job is NULL");
@@ -877,14 +877,18 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t N = b->n_atoms, S = b->S, G = b->n_seg;
     const int variant = id_class ? 1 : 0;
-    const bool frames = xyz3 != nullptr;
-    size_t fN = 0;  // atoms per frame
-    if (frames) {
+    const bool indexed = xyz3 != nullptr && ridx != nullptr;   // 13 B/atom: coordinates + a palette index per atom
+    const bool frames = xyz3 != nullptr;                       // any 12-byte coordinate form
+    size_t fN = 0;  // atoms per frame (MD form) / palette entries (indexed form)
+    if (indexed) {
+        fN = n_palette;
+    } else if (frames) {
         fN = S ? b->h_off[1] - b->h_off[0] : 0;
         for (size_t s = 0; s < S; ++s)
             if (b->h_off[s + 1] - b->h_off[s] != fN)
                 return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "run_frames needs equal-sized structures");
     }
+    if (indexed && (n_palette == 0 || n_palette > 256)) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "the radius palette holds 1..256 entries");
     const Points *pts = nullptr;
     if ((rc = get_points(ctx, params->n_points, &pts)) != 0) return rc;
     sasa_b200_job *job = job_acquire(ctx);
@@ -899,6 +903,7 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
     const size_t o_xyzr = o;   o += al(N * 16);
     const size_t o_xyz3 = o;   o += frames ? al(N * 12) : 0;
     const size_t o_rad = o;    o += frames ? al(fN * 4) : 0;
+    const size_t o_ridx = o;   o += indexed ? al(N) : 0;
     const size_t o_cls = o;    o += id_class ? al(N * 4) : 0;
     const size_t o_cnt = o;    o += out->counts ? al(N * 4) : 0;
     const size_t o_atom = o;   o += out->atom_sasa ? al(N * 4) : 0;
@@ -947,6 +952,7 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
     if (fused_frames) {
         kbase.xyz3 = reinterpret_cast<const float *>(base_p + o_xyz3);
         kbase.radii = reinterpret_cast<const float *>(base_p + o_rad);
+        if (indexed) kbase.ridx = reinterpret_cast<const uint8_t *>(base_p + o_ridx);
     }
     J_TRY(cudaMemsetAsync(d_status, 0, 32, s0));
     if (b->n_counters[variant]) J_TRY(cudaMemsetAsync(b->d_counters, 0, b->n_counters[variant] * sizeof(uint32_t), s0));
@@ -962,10 +968,16 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
         if (na) {
             if (frames) {
                 J_TRY(cudaMemcpyAsync(base_p + o_xyz3 + ch.a0 * 12, xyz3 + ch.a0 * 3, na * 12, cudaMemcpyHostToDevice, st));
+                if (indexed) J_TRY(cudaMemcpyAsync(base_p + o_ridx + ch.a0, ridx + ch.a0, na, cudaMemcpyHostToDevice, st));
                 if (!fused_frames) {
-                    pack_frames_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(
-                        reinterpret_cast<const float *>(base_p + o_xyz3) + ch.a0 * 3, reinterpret_cast<const float *>(base_p + o_rad),
-                        reinterpret_cast<float4 *>(base_p + o_xyzr) + ch.a0, (uint32_t)na, (uint32_t)fN, (uint32_t)(ch.a0 % (fN ? fN : 1)));
+                    if (indexed)
+                        pack_indexed_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(
+                            reinterpret_cast<const float *>(base_p + o_xyz3) + ch.a0 * 3, reinterpret_cast<const uint8_t *>(base_p + o_ridx) + ch.a0,
+                            reinterpret_cast<const float *>(base_p + o_rad), reinterpret_cast<float4 *>(base_p + o_xyzr) + ch.a0, (uint32_t)na);
+                    else
+                        pack_frames_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(
+                            reinterpret_cast<const float *>(base_p + o_xyz3) + ch.a0 * 3, reinterpret_cast<const float *>(base_p + o_rad),
+                            reinterpret_cast<float4 *>(base_p + o_xyzr) + ch.a0, (uint32_t)na, (uint32_t)fN, (uint32_t)(ch.a0 % (fN ? fN : 1)));
                     ++job->launches;
                 }
             } else {
@@ -1053,6 +1065,23 @@ int sasa_b200_batch_submit_frames_host(sasa_b200_batch *b, const float *xyz, con
     if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
     if (!xyz || !radii) return fail(b->ctx, SASA_B200_ERR_INVALID_ARGUMENT, "xyz / radii is NULL");
     return submit_host_impl(b, nullptr, xyz, radii, nullptr, params, out, out_job);
+}
+
+int sasa_b200_batch_submit_indexed_host(sasa_b200_batch *b, const float *xyz, const uint8_t *radius_index, const float *palette,
+                                        size_t n_palette, const uint32_t *id_class, const sasa_b200_params *params,
+                                        const sasa_b200_outputs *out, sasa_b200_job **out_job) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    if (b->n_atoms && (!xyz || !radius_index || !palette)) return fail(b->ctx, SASA_B200_ERR_INVALID_ARGUMENT, "xyz / radius_index / palette is NULL");
+    return submit_host_impl(b, nullptr, xyz, palette, id_class, params, out, out_job, radius_index, n_palette);
+}
+
+int sasa_b200_batch_run_indexed_host(sasa_b200_batch *b, const float *xyz, const uint8_t *radius_index, const float *palette,
+                                     size_t n_palette, const uint32_t *id_class, const sasa_b200_params *params,
+                                     const sasa_b200_outputs *out, sasa_b200_stats *stats) {
+    sasa_b200_job *job = nullptr;
+    int rc = sasa_b200_batch_submit_indexed_host(b, xyz, radius_index, palette, n_palette, id_class, params, out, &job);
+    if (rc) return rc;
+    return wait_job_impl(job, stats);
 }
 
 int sasa_b200_job_wait(sasa_b200_job *job, sasa_b200_stats *stats) {

@@ -37,6 +37,7 @@ struct KParams {
     // batch (device pointers)
     const float4 *xyzr;
     const float *xyz3, *radii;    // MD form (fused kernels only): 3 floats per atom + per-frame-index radii; else null
+    const uint8_t *ridx;          // indexed form: 3 floats per atom (xyz3) + one byte per atom into the palette `radii`; else null
     const uint32_t *cls;          // nullable
     const uint32_t *struct_off;   // S+1
     const uint32_t *order;        // structures handled by this launch

@@ -716,6 +716,14 @@ __global__ void __launch_bounds__(256) pack_frames_kernel(const float *__restric
     out[i] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __ldg(radii + a));
 }
 
+// xyz[atom][3] + one palette index per atom -> float4 {x, y, z, palette[index]}.
+__global__ void __launch_bounds__(256) pack_indexed_kernel(const float *__restrict__ xyz, const uint8_t *__restrict__ ridx,
+                                                           const float *__restrict__ palette, float4 *__restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __ldg(palette + ridx[i]));
+}
+
 inline void large_release(LargeWorkspace &w) {
     cudaFree(w.sorted); cudaFree(w.orig); cudaFree(w.cellid); cudaFree(w.rank); cudaFree(w.cls_sorted);
     cudaFree(w.bstart); cudaFree(w.val); cudaFree(w.zero_block);
@@ -775,9 +783,10 @@ inline int large_enqueue(int sm_count, LargeWorkspace &w, const KParams &kp, con
         large_bounds_kernel<<<gb, 256, 0, st>>>(at, N, w.hdr);
         large_count_kernel<<<gc, 256, 0, st>>>(at, N, w.hdr, kp.probe, cmax, kp.err_flag, w.cells, w.cellid, w.rank);
         // atoms per work block: kLBlock for structures that fill the machine, fewer for small ones so that every resident warp
-        // gets work (a 2,600-atom structure in blocks of 8 would occupy 7 % of the warp slots)
+        // slot sees eight blocks or more (a 2,600-atom structure in blocks of 8 would occupy 7 % of the warp slots; an eighth
+        // of the 1M-atom capsid in blocks of 8 is 3.3 blocks per slot: a fifth of the kernel was the wait for the 4-block warps)
         const int owned = (int)(((uint64_t)N + range_n - 1) / range_n);
-        const uint32_t blk = (uint32_t)std::max(1, std::min(kLBlock, owned / (sm_count * 32)));
+        const uint32_t blk = (uint32_t)std::max(1, std::min(kLBlock, owned / (sm_count * 32 * 8)));
         large_scan_kernel<<<gs, 256, 0, st>>>(w.hdr, w.cells, w.tiles, w.bstart, (uint32_t)N, blk);
         large_scatter_kernel<<<gc, 256, 0, st>>>(at, cls, N, w.hdr, w.cells, w.cellid, w.rank, w.sorted, w.orig, w.cls_sorted);
         const bool table = (kp.n_points <= 128 && kp.cap) || (kp.n_points > 128 && kp.n_points <= 1024 && kp.capm_in);

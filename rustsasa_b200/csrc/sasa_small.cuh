@@ -102,12 +102,18 @@ __device__ __forceinline__ void block_minmax8(float (&v)[8], float *red) {
     __syncthreads();
 }
 
-// Atom i of the structure that starts at a0: packed float4, or -- MD-trajectory form -- 12-byte coordinates plus the
-// radius table shared by all frames (what sasa_b200_batch_run_frames_host uploads; no intermediate float4 copy).
+// Radius of atom i of the structure that starts at a0 in the two 12-byte forms: the frame-shared radius table (MD), or a
+// palette indexed by one byte per atom (13 B/atom on the wire: what proteins with ProtOr radii need).
+__device__ __forceinline__ float load_radius3(const KParams &p, uint32_t a0, int i) {
+    return p.ridx ? __ldg(p.radii + __ldg(p.ridx + (size_t)a0 + (size_t)i)) : __ldg(p.radii + i);
+}
+
+// Atom i of the structure that starts at a0: packed float4, or -- MD-trajectory / indexed form -- 12-byte coordinates plus
+// the radius table (what sasa_b200_batch_run_frames_host / _run_indexed_host upload; no intermediate float4 copy).
 __device__ __forceinline__ float4 load_atom(const KParams &p, uint32_t a0, int i) {
     if (p.xyz3) {
         const float *q = p.xyz3 + 3 * ((size_t)a0 + (size_t)i);
-        return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(p.radii + i));
+        return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), load_radius3(p, a0, i));
     }
     return __ldg(p.xyzr + a0 + i);
 }
@@ -315,7 +321,7 @@ __device__ __forceinline__ void structure_outputs(const KParams &p, const SmemVi
     } else {
         for (int i = tid; i < N; i += NT) {
             const float cnt = V.val[i];
-            const float area = atom_area(p.xyz3 ? __ldg(p.radii + i) : __ldg(p.xyzr + a0 + i).w, p.probe, cnt, p.inv_n);
+            const float area = atom_area(p.xyz3 ? load_radius3(p, a0, i) : __ldg(p.xyzr + a0 + i).w, p.probe, cnt, p.inv_n);
             if (p.out_counts) p.out_counts[a0 + i] = (uint32_t)cnt;
             if (p.out_atom) p.out_atom[a0 + i] = area;
             V.val[i] = area;

@@ -55,6 +55,15 @@ def _stream(stream) -> int:
     return int(stream)
 
 
+def index_radii(radii):
+    """Palette + one-byte indices of a radius column (the indexed-radius wire format), or None when it holds more than 256
+    distinct values."""
+    pal, idx = np.unique(np.asarray(radii, np.float32), return_inverse=True)
+    if pal.shape[0] > 256:
+        return None
+    return pal.astype(np.float32), idx.astype(np.uint8)
+
+
 def _np(a, dtype, shape=None):
     if a is None:
         return None
@@ -222,6 +231,24 @@ class Batch:
         st = _lib.Stats()
         self.engine._check(self._L.sasa_b200_batch_run_frames_host(self._h, _ptr(xyz), _ptr(radii), C.byref(prm),
                                                                   C.byref(outs), C.byref(st)))
+        res.stats = st.as_dict()
+        return res
+
+    def run_indexed_host(self, xyz, radius_index, palette, id_class=None, probe_radius=1.4, n_points=100, simd_lanes=8, flags=0,
+                         want=("counts", "atom", "seg", "protein"), result: Optional[BatchResult] = None) -> BatchResult:
+        """Indexed-radius form (13 B/atom on the wire): xyz (N, 3) float32, radius_index (N,) uint8 into palette (<= 256,)."""
+        xyz = _np(xyz, np.float32, (-1, 3))
+        radius_index = _np(radius_index, np.uint8)
+        palette = _np(palette, np.float32)
+        assert xyz.shape[0] == self.n_atoms == radius_index.shape[0]
+        id_class = _np(id_class, np.uint32)
+        res = result if result is not None else self._host_outputs(want, "numpy")
+        outs = _lib.Outputs(_ptr(res.counts), _ptr(res.atom_sasa), _ptr(res.seg_sasa), _ptr(res.protein))
+        prm = self._params(probe_radius, n_points, simd_lanes, flags)
+        st = _lib.Stats()
+        self.engine._check(self._L.sasa_b200_batch_run_indexed_host(self._h, _ptr(xyz), _ptr(radius_index), _ptr(palette),
+                                                                   palette.shape[0], _ptr(id_class), C.byref(prm), C.byref(outs),
+                                                                   C.byref(st)))
         res.stats = st.as_dict()
         return res
 

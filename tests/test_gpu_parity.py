@@ -684,3 +684,35 @@ def test_full_size_configs_match_oracle_fingerprints(eng):
         assert np.array_equal(parts[0].counts + parts[1].counts + parts[2].counts, r.counts)
         assert np.array_equal(parts[0].atom_sasa + parts[1].atom_sasa + parts[2].atom_sasa, r.atom_sasa)
         b.close()
+
+
+def test_indexed_radius_wire_format_equals_float4(eng, golden):
+    """sasa_b200_batch_run_indexed_host (12 B coordinates + 1 B palette index per atom) gives the float4 form's results bit for
+    bit: a proteome sample through the fused kernels (all levels, with id classes too) and a batch with a large structure."""
+    from rustsasa_b200 import SasaB200Error
+    from rustsasa_b200 import workloads as W
+    from rustsasa_b200.engine import index_radii
+    d = W.proteome_batch(40, seed=77)
+    pal, idx = index_radii(d.xyzr[:, 3])
+    assert pal.shape[0] <= 16
+    b = eng.batch(d.struct_off, d.seg_be, d.struct_seg_off, d.seg_polar)
+    ref = b.run_host(d.xyzr)
+    got = b.run_indexed_host(d.xyzr[:, :3], idx, pal)
+    for k in ("counts", "atom_sasa", "seg_sasa", "protein"):
+        assert np.array_equal(getattr(ref, k), getattr(got, k)), k
+    cls = np.arange(d.n_atoms, dtype=np.uint32)
+    cls[1] = cls[0]
+    assert np.array_equal(b.run_indexed_host(d.xyzr[:, :3], idx, pal, id_class=cls).counts, b.run_host(d.xyzr, id_class=cls).counts)
+    with pytest.raises(SasaB200Error):
+        b.run_indexed_host(d.xyzr[:, :3], idx, np.zeros(300, np.float32))
+    b.close()
+    big = W.large_assembly(9000)
+    s = golden.structure("example.cif")
+    xyzr = np.concatenate([s["xyzr"], big.xyzr])
+    off = np.array([0, s["xyzr"].shape[0], xyzr.shape[0]], np.uint64)
+    pal, idx = index_radii(xyzr[:, 3])
+    b = eng.batch(off)
+    ref = b.run_host(xyzr, want=("counts", "atom"))
+    got = b.run_indexed_host(xyzr[:, :3], idx, pal, want=("counts", "atom"))
+    assert np.array_equal(ref.counts, got.counts) and np.array_equal(ref.atom_sasa, got.atom_sasa)
+    b.close()
