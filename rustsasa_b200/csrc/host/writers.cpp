@@ -1,7 +1,7 @@
 // writers.cpp -- result serialisation, src/utils/io.rs:11-18.
 //
 // JSON is serde_json's rendering of the externally tagged `SASAResult` enum (src/structures/atomic.rs:62-70), fields in
-// declaration order, f32 printed shortest-round-trip like ryu ("25.0", "0.0", "1e-7").  XML follows quick-xml's serde
+// declaration order, f32 printed shortest-round-trip like ryu ("25.0", "0.0", "1e-7"; XML prints the same digits the way Rust's Display does: "25", "0", "0.0000001").  XML follows quick-xml's serde
 // serializer: a newtype variant holding a sequence becomes one element per item named after the variant.  The XML
 // shape could not be checked against the crate here (no Rust toolchain); the JSON shape is pinned by the reference's
 // own test helpers (tests/common/io.rs).  B-factor write-back (src/utils/io.rs:20-64) and the coordinate-section writers after
@@ -74,10 +74,26 @@ std::string xml_text(const std::string &s) {
     return o;
 }
 
+// f32 the way quick-xml's serde serializer writes primitives: `value.to_string()`, i.e. Rust's Display for f32 -- the
+// shortest round-trip digits laid out positionally, never with an exponent and without a trailing ".0" ("25", "0.1",
+// "0.0000001", "15000000000"); NaN / inf / -inf by name.  (serde_json, above, prints the same digits ryu-style.)
 std::string xml_f32(float v) {
     if (std::isnan(v)) return "NaN";
     if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
-    return fmt_f32(v);
+    if (v == 0.0f) return std::signbit(v) ? "-0" : "0";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, std::fabs(v), std::chars_format::scientific);
+    const std::string sci(buf, r.ptr);
+    const size_t e = sci.find('e');
+    std::string digits;
+    for (char c : sci.substr(0, e))
+        if (c != '.') digits += c;
+    const int kk = std::atoi(sci.c_str() + e + 1) + 1, len = (int)digits.size();   // value = 0.DIGITS x 10^kk
+    std::string out = std::signbit(v) ? "-" : "";
+    if (kk >= len) out += digits + std::string((size_t)(kk - len), '0');
+    else if (kk > 0) out += digits.substr(0, (size_t)kk) + "." + digits.substr((size_t)kk);
+    else out += "0." + std::string((size_t)(-kk), '0') + digits;
+    return out;
 }
 
 }  // namespace

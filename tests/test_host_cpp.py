@@ -144,7 +144,11 @@ def test_writers(host):
     x = host.format_values([3.5, 1.25, 2.25], xml=True, kind="protein")
     assert x == ("<Protein><global_total>3.5</global_total><polar_total>1.25</polar_total>"
                  "<non_polar_total>2.25</non_polar_total></Protein>")
-    assert host.format_values([1.0, 2.5], xml=True) == "<Atom>1.0</Atom><Atom>2.5</Atom>"
+    # quick-xml writes primitives with `to_string()` (Rust's Display): shortest digits, no exponent, no trailing ".0"
+    assert host.format_values([1.0, 2.5, 1e-7, 1.5e10, 0.0], xml=True) == \
+        "<Atom>1</Atom><Atom>2.5</Atom><Atom>0.0000001</Atom><Atom>15000000000</Atom><Atom>0</Atom>"
+    back = np.array([float(t) for t in host.format_values(v, xml=True).replace("</Atom>", "").split("<Atom>")[1:]], np.float32)
+    assert np.array_equal(back, v)
 
 
 def test_cli_argument_errors(host, tmp_path):
