@@ -356,6 +356,9 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const Ato
 }
 
 // ---- chunked cap tables: 128 < n_points <= 1024 --------------------------------------------------------------------------
+#ifndef SASA_CAPM_UNROLL
+#define SASA_CAPM_UNROLL 2     // pass-1 loop unroll.  Measured on cfg5 (gpurun_out r02l): 2 -> 1.60 ms, 4 -> 1.93 ms (spills), 8 -> 1.62 ms;
+#endif                         // a 96^2 / 128^2 direction grid gives 1.55 / 1.54 ms for 2.3x / 4x the table (kept at 64^2)
 // Bin of entry e with run-time grid dimensions (same arithmetic as cap_bin).
 __device__ __forceinline__ unsigned cap_bin_rt(const float4 e, float vmag, const CapDims &D) {
     const float c = e.w * cap_rsqrt(vmag);
@@ -410,7 +413,8 @@ __device__ __forceinline__ int capm_atom(const uint4 *__restrict__ tin, const ui
         vm[w] = left >= 32 ? 0xffffffffu : (left > 0 ? (0xffffffffu >> (32 - left)) : 0u);
     }
     unsigned a[4] = {0u, 0u, 0u, 0u};
-#pragma unroll 2
+    constexpr int kFetchUnroll = SASA_CAPM_UNROLL;
+#pragma unroll kFetchUnroll
     for (int q0 = 0; q0 < k; q0 += PER) {
         const int q = q0 + sub;
         if (q < k) {
