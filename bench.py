@@ -443,6 +443,31 @@ def secondary_configs(args, eng, rank, world, local_rank, weak_seg_rank0):
         g = golden["cfg5"]
         got = counts.cpu().numpy().view(np.uint32)
         ok = NA == g["atoms"] and int(got.astype(np.int64).sum()) == g["sum_counts"] and sha_counts(got) == g["sha256_counts"]
+        # the exchange fused into the kernel: every rank writes its atoms' values into all ranks' vectors over NVLink
+        # (torch symmetric memory), no zero-fill, no all-reduce; a barrier on either side
+        fused = None
+        if world > 1:
+            try:
+                from rustsasa_b200.shard import PeerVectors, run_atom_range_peers
+                pv = PeerVectors(NA)
+
+                def step_peers():
+                    run_atom_range_peers(lambda r, w, v: b.run_atom_range_peers_device(d_x, r, w, v.count_ptrs, v.atom_ptrs, n_points=960), pv)
+                for _ in range(3):
+                    step_peers()
+                p_ms = timed_events(step_peers, 5)
+                p_wall = timed_wall(step_peers, 5)
+                pv.counts.zero_()
+                torch.cuda.synchronize()
+                barrier()
+                step_peers()
+                torch.cuda.synchronize()
+                got_p = pv.counts.cpu().numpy().view(np.uint32)
+                okp = bool(np.array_equal(got_p, got))
+                fused = {"value": NA / (p_ms * 1e-3), "ms_per_step": p_ms, "wall_ms_per_step": p_wall, "parity": allr(okp),
+                         "note": "sasa_b200_batch_run_atom_range_peers_device: peer stores from inside the atoms kernel + two barriers"}
+            except Exception as e:
+                fused = {"error": repr(e)}
         out["cfg5_capsid"] = {
             "workload": f"one {NA}-atom capsid shell, AtomLevel, 960 points; every rank builds the whole cell list and evaluates its "
                         f"interleaved share of the cell-sorted atoms; per-rank count / area vectors summed by ncclAllReduce ({world} GPU(s))",
@@ -451,6 +476,8 @@ def secondary_configs(args, eng, rank, world, local_rank, weak_seg_rank0):
             "wall": {"value": NA / (wall_ms * 1e-3), "ms_per_step": wall_ms}, "unit": UNIT, "parity": allr(ok),
             "parity_against": "sha256 + sum of the oracle's per-atom counts at full size (tests/golden/cfg_hashes.json), exact",
             "sum_counts": int(got.astype(np.int64).sum())}
+        if fused is not None:
+            out["cfg5_capsid"]["peer_writes"] = fused
         b.close()
     except Exception as e:
         out["cfg5_capsid"] = {"error": repr(e)}

@@ -205,6 +205,15 @@ SASA_B200_API int sasa_b200_batch_submit_indexed_host(sasa_b200_batch *batch, co
 SASA_B200_API int sasa_b200_batch_run_atom_range_device(sasa_b200_batch *batch, const float *d_xyzr, const uint32_t *d_id_class,
                                           const sasa_b200_params *params, uint32_t rank, uint32_t n_ranks,
                                           uint32_t *d_counts /* nullable */, float *d_atom_sasa /* nullable */, void *stream);
+/* The same with the exchange step fused into the kernel: peer_counts[r] / peer_atom_sasa[r] (host arrays of n_ranks device
+ * pointers, each valid on THIS device -- the local vector for r == rank, the peers' vectors mapped over NVLink / NVSwitch,
+ * e.g. the buffer_ptrs of a torch symmetric-memory allocation or cudaIpc handles) receive the values of the atoms this rank
+ * owns as they are produced.  Nothing is zero-filled and nothing is reduced afterwards: once every rank's kernel has finished
+ * (a barrier across ranks, not provided here) every rank holds the complete vectors.  Either array may be NULL; n_ranks <= 8.
+ * The caller also keeps ranks from overwriting vectors a peer is still reading (a barrier before the call). */
+SASA_B200_API int sasa_b200_batch_run_atom_range_peers_device(sasa_b200_batch *batch, const float *d_xyzr, const uint32_t *d_id_class,
+                                                const sasa_b200_params *params, uint32_t rank, uint32_t n_ranks,
+                                                uint32_t *const *peer_counts, float *const *peer_atom_sasa, void *stream);
 SASA_B200_API int sasa_b200_batch_run_atom_range_host(sasa_b200_batch *batch, const float *xyzr, const uint32_t *id_class,
                                         const sasa_b200_params *params, uint32_t rank, uint32_t n_ranks,
                                         uint32_t *out_counts /* nullable */, float *out_atom_sasa /* nullable */,

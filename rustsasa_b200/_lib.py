@@ -25,6 +25,7 @@ EXPORTS = [
     "sasa_b200_batch_run_atom_range_host", "sasa_b200_batch_reduce_device",
     "sasa_b200_batch_submit_host", "sasa_b200_batch_submit_frames_host", "sasa_b200_job_wait",
     "sasa_b200_device_count", "sasa_b200_batch_run_indexed_host", "sasa_b200_batch_submit_indexed_host",
+    "sasa_b200_batch_run_atom_range_peers_device",
 ]
 
 
@@ -87,6 +88,7 @@ def load() -> C.CDLL:
     L.sasa_b200_batch_run_atom_range_device.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, C.c_uint32, vp, vp, vp]
     L.sasa_b200_batch_run_atom_range_host.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, C.c_uint32, vp, vp,
                                                       C.POINTER(Stats)]
+    L.sasa_b200_batch_run_atom_range_peers_device.argtypes = [vp, vp, vp, C.POINTER(Params), C.c_uint32, C.c_uint32, vp, vp, vp]
     L.sasa_b200_batch_reduce_device.argtypes = [vp, vp, vp, vp, vp]
     L.sasa_b200_run_batch.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, C.POINTER(Params), C.POINTER(Outputs),
                                       C.POINTER(Stats)]

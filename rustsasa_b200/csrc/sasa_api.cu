@@ -1106,7 +1106,8 @@ int sasa_b200_batch_run_frames_host(sasa_b200_batch *b, const float *xyz, const 
 // slice `rank` of `n_ranks` of its cell-sorted atom order is evaluated.  Outputs are zero-filled first, so summing
 // the per-rank vectors (ncclAllReduce over NVLink, or on the host) reproduces the single-GPU result bit for bit.
 static int run_atom_range_locked(sasa_b200_batch *b, const float *d_xyzr, const uint32_t *d_cls, const sasa_b200_params *params,
-                                 uint32_t rank, uint32_t n_ranks, uint32_t *d_counts, float *d_atom, cudaStream_t st) {
+                                 uint32_t rank, uint32_t n_ranks, uint32_t *d_counts, float *d_atom, cudaStream_t st,
+                                 uint32_t *const *peer_counts = nullptr, float *const *peer_atom = nullptr) {
     sasa_b200_ctx *ctx = b->ctx;
     int rc = check_params(ctx, params);
     if (rc) return rc;
@@ -1129,8 +1130,21 @@ static int run_atom_range_locked(sasa_b200_batch *b, const float *d_xyzr, const 
     kp.seg_be = nullptr;
     kp.out_seg = nullptr;
     b->launches_last = 0;
-    if (d_counts && b->n_atoms) CU_TRY(ctx, cudaMemsetAsync(d_counts, 0, b->n_atoms * sizeof(uint32_t), st));
-    if (d_atom && b->n_atoms) CU_TRY(ctx, cudaMemsetAsync(d_atom, 0, b->n_atoms * sizeof(float), st));
+    const bool peers = peer_counts != nullptr || peer_atom != nullptr;
+    if (peers) {
+        // every atom's owner writes it into every rank's vectors: nothing to zero, nothing to reduce afterwards
+        if (n_ranks > 8) return fail(ctx, SASA_B200_ERR_UNSUPPORTED, "peer writes support at most 8 ranks, got %u", n_ranks);
+        kp.n_peers = (int)n_ranks;
+        for (uint32_t r = 0; r < n_ranks; ++r) {
+            kp.peer_counts[r] = peer_counts ? peer_counts[r] : nullptr;
+            kp.peer_atom[r] = peer_atom ? peer_atom[r] : nullptr;
+        }
+        kp.out_counts = peer_counts ? peer_counts[rank] : nullptr;   // the local vectors (non-finite input blanks them)
+        kp.out_atom = peer_atom ? peer_atom[rank] : nullptr;
+    } else {
+        if (d_counts && b->n_atoms) CU_TRY(ctx, cudaMemsetAsync(d_counts, 0, b->n_atoms * sizeof(uint32_t), st));
+        if (d_atom && b->n_atoms) CU_TRY(ctx, cudaMemsetAsync(d_atom, 0, b->n_atoms * sizeof(float), st));
+    }
     std::vector<uint32_t> order(b->S);
     std::iota(order.begin(), order.end(), 0u);
     if (ctx->large_used) CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_large, 0));
@@ -1154,6 +1168,19 @@ int sasa_b200_batch_run_atom_range_device(sasa_b200_batch *b, const float *d_xyz
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     return run_atom_range_locked(b, d_xyzr, d_id_class, params, rank, n_ranks, d_counts, d_atom_sasa,
                                  stream ? (cudaStream_t)stream : ctx->streams[0]);
+}
+
+int sasa_b200_batch_run_atom_range_peers_device(sasa_b200_batch *b, const float *d_xyzr, const uint32_t *d_id_class,
+                                                const sasa_b200_params *params, uint32_t rank, uint32_t n_ranks,
+                                                uint32_t *const *peer_counts, float *const *peer_atom_sasa, void *stream) {
+    if (!b) return SASA_B200_ERR_INVALID_ARGUMENT;
+    sasa_b200_ctx *ctx = b->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!d_xyzr && b->n_atoms) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "d_xyzr is NULL");
+    if (!peer_counts && !peer_atom_sasa) return fail(ctx, SASA_B200_ERR_INVALID_ARGUMENT, "peer_counts and peer_atom_sasa are both NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    return run_atom_range_locked(b, d_xyzr, d_id_class, params, rank, n_ranks, nullptr, nullptr,
+                                 stream ? (cudaStream_t)stream : ctx->streams[0], peer_counts, peer_atom_sasa);
 }
 
 int sasa_b200_batch_run_atom_range_host(sasa_b200_batch *b, const float *xyzr, const uint32_t *id_class,

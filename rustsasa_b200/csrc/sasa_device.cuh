@@ -51,6 +51,11 @@ struct KParams {
     float *out_atom;
     float *out_seg;
     float *out_protein;
+    // atom-range split with peer writes: the per-atom outputs of this rank's share go straight into every rank's vectors
+    // (pointers valid on THIS device: the local vector and the peers' over NVLink); n_peers = 0: out_counts / out_atom only
+    uint32_t *peer_counts[8];
+    float *peer_atom[8];
+    int n_peers;
     // sphere points (SoA) and run parameters
     const float *px, *py, *pz;
     const uint4 *cap;             // cap table of this point set (sasa_cap.cuh), n_points <= 128 only; else null

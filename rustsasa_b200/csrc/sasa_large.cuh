@@ -257,6 +257,23 @@ __device__ __forceinline__ unsigned large_owned_block(unsigned t, unsigned rank,
     return ((t / kLGroup) * n_ranks + rank) * kLGroup + (t % kLGroup);
 }
 
+// Result of one atom (all lanes hold the same values).  Plain run: lane 0 writes the local outputs.  Atom-range split with peer
+// writes: lane r writes rank r's vectors -- the local one and, over NVLink, the peers' -- so that when every rank's kernel has
+// finished each rank holds the complete vectors and no all-reduce (nor its zero-fill) is needed: the exchange step of the
+// split is fused into the kernel that produces the values.
+__device__ __forceinline__ void large_store(const KParams &p, int lane, uint32_t gi, uint32_t oi, float *val, float area, uint32_t cnt) {
+    if (lane == 0) val[oi] = area;
+    if (p.n_peers > 0) {
+        if (lane < p.n_peers) {
+            if (p.peer_counts[lane]) p.peer_counts[lane][gi] = cnt;
+            if (p.peer_atom[lane]) p.peer_atom[lane][gi] = area;
+        }
+    } else if (lane == 0) {
+        if (p.out_counts) p.out_counts[gi] = cnt;
+        if (p.out_atom) p.out_atom[gi] = area;
+    }
+}
+
 // Non-finite input: the reference panics; every output of the structure is blanked instead (quiet NaN, counts 0).
 __device__ __forceinline__ void large_blank_outputs(const KParams &p, int N, uint32_t a0) {
     const float qn = __int_as_float(0x7fc00000);
@@ -264,6 +281,7 @@ __device__ __forceinline__ void large_blank_outputs(const KParams &p, int N, uin
         if (p.out_counts) p.out_counts[a0 + i] = 0u;
         if (p.out_atom) p.out_atom[a0 + i] = qn;
     }
+    // (with peer writes every rank detects the bad input itself and blanks its own vectors: out_* are the local ones)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -463,13 +481,7 @@ __global__ void __launch_bounds__(256, 4) large_cells_kernel(const KParams p, in
                     __syncwarp();
                     if (pos + 1 < cell_end) total = large_stage(g, cells, sorted, cx, cy, cz, st, self0);
                 }
-                if (lane == 0) {
-                    const uint32_t oi = __ldg(orig + pos);
-                    const float area = atom_area(radius, p.probe, (float)cnt, p.inv_n);
-                    val[oi] = area;
-                    if (p.out_counts) p.out_counts[a0 + oi] = (uint32_t)cnt;
-                    if (p.out_atom) p.out_atom[a0 + oi] = area;
-                }
+                large_store(p, lane, a0 + __ldg(orig + pos), __ldg(orig + pos), val, atom_area(radius, p.probe, (float)cnt, p.inv_n), (uint32_t)cnt);
                 __syncwarp();
             }
         }
@@ -547,13 +559,7 @@ __global__ void __launch_bounds__(256, 2) large_atoms_kernel(const KParams p, in
                             : atom_streaming<GlobalAtoms, uint32_t, false>(p, g, atoms, cells, cls_sorted, pos, w_ent, p.stat);
                 streamed += 1;
             }
-            if (lane == 0) {
-                const uint32_t oi = orig[pos];
-                const float area = atom_area(ai.w, p.probe, cnt, p.inv_n);
-                val[oi] = area;
-                if (p.out_counts) p.out_counts[a0 + oi] = (uint32_t)cnt;
-                if (p.out_atom) p.out_atom[a0 + oi] = area;
-            }
+            large_store(p, lane, a0 + orig[pos], orig[pos], val, atom_area(ai.w, p.probe, cnt, p.inv_n), (uint32_t)cnt);
             __syncwarp();
         }
     }

@@ -270,6 +270,16 @@ class Batch:
             self._h, _ptr(d_xyzr), _ptr(d_id_class), C.byref(prm), rank, n_ranks, _ptr(counts), _ptr(atom_sasa),
             _stream(stream)))
 
+    def run_atom_range_peers_device(self, d_xyzr, rank: int, n_ranks: int, peer_counts=None, peer_atom_sasa=None, d_id_class=None,
+                                    probe_radius=1.4, n_points=100, simd_lanes=8, stream=None):
+        """Atom-range split with the exchange fused into the kernel: peer_counts / peer_atom_sasa are sequences of n_ranks
+        raw device pointers (ints), valid on this device, of every rank's output vector (symmetric-memory buffer_ptrs)."""
+        prm = self._params(probe_radius, n_points, simd_lanes, 0)
+        pc = (C.c_void_p * n_ranks)(*[int(x) for x in peer_counts]) if peer_counts is not None else None
+        pa = (C.c_void_p * n_ranks)(*[int(x) for x in peer_atom_sasa]) if peer_atom_sasa is not None else None
+        self.engine._check(self._L.sasa_b200_batch_run_atom_range_peers_device(
+            self._h, _ptr(d_xyzr), _ptr(d_id_class), C.byref(prm), rank, n_ranks, pc, pa, _stream(stream)))
+
     def run_atom_range_host(self, xyzr, rank: int, n_ranks: int, id_class=None, probe_radius=1.4, n_points=100,
                             simd_lanes=8) -> BatchResult:
         xyzr = _np(xyzr, np.float32, (-1, 4))

@@ -191,3 +191,37 @@ def run_atom_range(compute_range: Callable[[int, int], Tuple["object", "object"]
         w1.wait()
         w2.wait()
     return counts, atom_sasa
+
+
+class PeerVectors:
+    """Per-atom output vectors of an atom-range split in torch symmetric memory: every rank allocates the same two vectors,
+    the rendezvous maps all of them into every rank's address space (NVLink / NVSwitch peer memory), and each rank's atoms
+    kernel writes the values of the atoms it owns straight into all of them (`Batch.run_atom_range_peers_device`) -- the
+    all-reduce of `run_atom_range` and its zero-fill disappear; what remains is a barrier on either side."""
+
+    def __init__(self, n_atoms: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.counts = symm_mem.empty(n_atoms, dtype=torch.int32, device="cuda")
+        self.atom_sasa = symm_mem.empty(n_atoms, dtype=torch.float32, device="cuda")
+        self._hc = symm_mem.rendezvous(self.counts, self.group)
+        self._ha = symm_mem.rendezvous(self.atom_sasa, self.group)
+        self.rank, self.world = self._hc.rank, self._hc.world_size
+        self.count_ptrs = list(self._hc.buffer_ptrs)
+        self.atom_ptrs = list(self._ha.buffer_ptrs)
+
+    def barrier(self):
+        """Cross-rank barrier on the current stream (signal pads of the symmetric allocation)."""
+        self._hc.barrier()
+
+
+def run_atom_range_peers(launch: Callable[[int, int, "PeerVectors"], None], peers: "PeerVectors"):
+    """One step of the atom-range split with peer writes: barrier (nobody still reads the vectors), this rank's kernels
+    (`launch(rank, world, peers)` enqueues `run_atom_range_peers_device` on the current stream), barrier (every rank's values
+    have landed).  Returns (counts, atom_sasa): complete on every rank, bit-identical to a single-GPU run."""
+    peers.barrier()
+    launch(peers.rank, peers.world, peers)
+    peers.barrier()
+    return peers.counts, peers.atom_sasa

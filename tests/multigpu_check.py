@@ -93,6 +93,21 @@ def main():
         torch.cuda.synchronize()
         assert np.array_equal(counts.cpu().numpy().view(np.uint32), single.counts)
         assert np.array_equal(atom.cpu().numpy(), single.atom_sasa)
+    # the same with the exchange fused into the kernel: every rank writes its atoms' values straight into all ranks' vectors
+    # (torch symmetric memory: NVLink peer pointers), no zero-fill and no all-reduce
+    from rustsasa_b200.shard import PeerVectors, run_atom_range_peers
+    peers = PeerVectors(a.n_atoms)
+    for _ in range(3):
+        pc, pa = run_atom_range_peers(
+            lambda r, w, pv: b.run_atom_range_peers_device(d_xyzr, r, w, pv.count_ptrs, pv.atom_ptrs, n_points=960), peers)
+        torch.cuda.synchronize()
+        assert np.array_equal(pc.cpu().numpy().view(np.uint32), single.counts)
+        assert np.array_equal(pa.cpu().numpy(), single.atom_sasa)
+        pc.zero_()
+        pa.zero_()
+        torch.cuda.synchronize()
+    if rank == 0:
+        print(f"atom-range split with peer writes over {world} GPUs: equals the single-GPU result (3 runs)", flush=True)
     # balance of the interleaved ownership: atoms evaluated by this rank
     mine, _ = compute_range_big(rank, world)
     part = b.run_atom_range_host(a.xyzr, rank, world, n_points=960)

@@ -30,3 +30,4 @@ def test_multigpu_check_on_all_gpus():
     assert f"sharded batch over {n} GPUs: parity OK" in r.stdout
     assert f"over {n} GPUs + all-reduce: parity OK" in r.stdout
     assert f"over {n} GPUs: equals the oracle fingerprint" in r.stdout
+    assert f"peer writes over {n} GPUs: equals the single-GPU result" in r.stdout

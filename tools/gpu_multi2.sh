@@ -18,5 +18,5 @@ import json
 d=json.load(open("$OUT/bench_${N}gpu.json"))
 print("N=%d value %.1f e2e %.1f binding %s"%(d["n_gpus"],d["value"]/1e6,d["e2e"]["value"]/1e6,d.get("host_binding")))
 for k,v in d.get("secondary",{}).items():
-    print(k, {kk:(round(vv/1e6,1) if kk=="value" else vv) for kk,vv in v.items() if kk in ("value","ms_per_step","parity","error","gather_ms","kernels_only","wall")}, "e2e", v.get("e2e"))
+    print(k, {kk:(round(vv/1e6,1) if kk=="value" else vv) for kk,vv in v.items() if kk in ("value","ms_per_step","parity","error","gather_ms","kernels_only","wall","peer_writes")}, "e2e", v.get("e2e"))
 PY
