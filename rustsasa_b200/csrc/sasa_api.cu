@@ -279,7 +279,8 @@ struct sasa_b200_batch {
     std::vector<Chunk> plan[4];
     std::vector<uint32_t> h_order[4];
     uint32_t n_counters[4] = {0, 0, 0, 0};
-    uint32_t max_large = 0;
+    uint32_t max_large = 0;             // largest structure that takes the large-structure path in ANY plan (workspace size)
+    uint32_t max_large_v[4] = {0, 0, 0, 0};   // ... per plan: a structure may fit the fused kernels without id classes only
     // device topology
     uint32_t *d_off = nullptr, *d_seg_off = nullptr, *d_order[4] = {nullptr, nullptr, nullptr, nullptr}, *d_counters = nullptr;
     uint2 *d_seg_be = nullptr;
@@ -356,7 +357,10 @@ void build_plan(sasa_b200_batch *b, int variant) {
             // one-structure convenience entry points ask for this; explicit batches keep the fused kernels.
             if (b->single_latency && b->S == 1 && n >= kSingleLargeMin) k = cap.size();
             bucket[k].push_back(i);
-            if (k == cap.size()) b->max_large = std::max(b->max_large, n);
+            if (k == cap.size()) {
+                b->max_large = std::max(b->max_large, n);
+                b->max_large_v[variant] = std::max(b->max_large_v[variant], n);
+            }
         }
         // One launch per chunk wherever that costs little: every extra bucket is an extra kernel with its own ramp-up
         // and tail (measured on the proteome batch: 953 vs 875 M atoms/s end to end).  If the widest fused
@@ -948,7 +952,9 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
     kbase.stat = d_status + 1;
     // MD form: the fused kernels read the 12-byte coordinates and the shared radius table directly; only batches with
     // structures on the large-structure path still expand to float4 first
-    const bool fused_frames = frames && b->max_large == 0;
+    // (per plan: round 1 asked "any plan", so a 5,001-atom frame -- fused without id classes, large path with them -- lost both
+    // the fused unpack and the three-stream overlap: cfg3 ran 18.4 ms end to end where the kernels take 12.9 ms)
+    const bool fused_frames = frames && b->max_large_v[variant] == 0;
     if (fused_frames) {
         kbase.xyz3 = reinterpret_cast<const float *>(base_p + o_xyz3);
         kbase.radii = reinterpret_cast<const float *>(base_p + o_rad);
@@ -961,7 +967,7 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
     for (int i = 1; i < kStreams; ++i) J_TRY(cudaStreamWaitEvent(ctx->streams[i], job->ev0, 0));
     size_t ci = 0;
     // the large-structure workspace is shared by all chunks: keep such batches on a single stream
-    const int nstreams = b->max_large ? 1 : kStreams;
+    const int nstreams = b->max_large_v[variant] ? 1 : kStreams;
     for (const Chunk &ch : b->plan[variant]) {
         cudaStream_t st = ctx->streams[ci++ % nstreams];
         const size_t na = ch.a1 - ch.a0;
