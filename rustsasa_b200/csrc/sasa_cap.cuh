@@ -383,7 +383,9 @@ __device__ __forceinline__ unsigned cap_bin_rt(const float4 e, float vmag, const
 //            case: 94 % of all points are) ends here with no point test at all
 //   pass 2   per (neighbour, chunk): ring points not yet covered take the reference's exact test; hits join the coverage
 // Returns the exposed-point count.  nb: candidate indices (into `atoms`) of the k <= 128 neighbours; nbp: 128 u32 of scratch.
-template <int NCHP, class Atoms, class IdxT>
+// IDX_BITS: width of a candidate index in the packed (bin, index) word: 9 for the staged strips of the large-structure path,
+// 13 for the shared-memory atoms of the fused kernel (bins need 19 bits at 64 x 64 x 66).
+template <int NCHP, int IDX_BITS, class Atoms, class IdxT>
 __device__ __forceinline__ int capm_atom(const uint4 *__restrict__ tin, const uint4 *__restrict__ trg, const CapDims &D,
                                          const Atoms &atoms, const float4 ai, float probe, const IdxT *nb, int k, uint32_t *nbp,
                                          const float4 *__restrict__ pts4, int n_points, int nbody) {
@@ -401,7 +403,7 @@ __device__ __forceinline__ int capm_atom(const uint4 *__restrict__ tin, const ui
             float vmag;
             const float4 e = make_entry(ai, atoms((int)j), probe, r2, two_r, &vmag);
             const unsigned bin = vmag >= kCapMinV2 ? cap_bin_rt(e, vmag, D) : D.bin_degenerate;
-            nbp[q] = (bin << 9) | j;
+            nbp[q] = (bin << IDX_BITS) | j;
         }
     }
     __syncwarp();
@@ -418,7 +420,7 @@ __device__ __forceinline__ int capm_atom(const uint4 *__restrict__ tin, const ui
     for (int q0 = 0; q0 < k; q0 += PER) {
         const int q = q0 + sub;
         if (q < k) {
-            const uint4 m = __ldg(tin + (((size_t)(nbp[q] >> 9)) << D.nchp_shift) + ch);
+            const uint4 m = __ldg(tin + (((size_t)(nbp[q] >> IDX_BITS)) << D.nchp_shift) + ch);
             a[0] |= m.x; a[1] |= m.y; a[2] |= m.z; a[3] |= m.w;
         }
     }
@@ -436,8 +438,8 @@ __device__ __forceinline__ int capm_atom(const uint4 *__restrict__ tin, const ui
         unsigned j = 0;
         if (q < k && open) {
             const unsigned pk = nbp[q];
-            j = pk & 511u;
-            const uint4 g = __ldg(trg + (((size_t)(pk >> 9)) << D.nchp_shift) + ch);
+            j = pk & ((1u << IDX_BITS) - 1u);
+            const uint4 g = __ldg(trg + (((size_t)(pk >> IDX_BITS)) << D.nchp_shift) + ch);
             m[0] = g.x & vm[0] & ~a[0]; m[1] = g.y & vm[1] & ~a[1]; m[2] = g.z & vm[2] & ~a[2]; m[3] = g.w & vm[3] & ~a[3];
         }
         if (!__any_sync(kFull, (m[0] | m[1] | m[2] | m[3]) != 0u)) continue;

@@ -469,8 +469,8 @@ __global__ void __launch_bounds__(256, 4) large_cells_kernel(const KParams p, in
                         if constexpr (NCHP == 1)
                             cnt = cap_atom(p.cap, StagedAtoms{st}, ai, p.probe, nb, k, s_ptab, (int)p.n_points, nbody);
                         else
-                            cnt = capm_atom<NCHP>(p.capm_in, p.capm_rg, p.capd, StagedAtoms{st}, ai, p.probe, nb, k, s_nbp[warp], p.pts4,
-                                                  (int)p.n_points, nbody);
+                            cnt = capm_atom<NCHP, 9>(p.capm_in, p.capm_rg, p.capd, StagedAtoms{st}, ai, p.probe, nb, k, s_nbp[warp], p.pts4,
+                                                     (int)p.n_points, nbody);
                         pairs += (unsigned)k;
                     }
                 }
@@ -798,11 +798,9 @@ inline int large_enqueue(int sm_count, LargeWorkspace &w, const KParams &kp, con
         const bool table = (kp.n_points <= 128 && kp.cap) || (kp.n_points > 128 && kp.n_points <= 1024 && kp.capm_in);
         if (!cls && (kp.flags & 3u) == 0 && table) {
             const int ga = std::max(1, std::min((owned + 8 * (int)blk - 1) / (8 * (int)blk), sm_count * 4));
-            const int shift = kp.n_points <= 128 ? 0 : kp.capd.nchp_shift;
+            // chunked tables are always laid out for eight chunks (the fused kernel shares them): one instantiation
 #define SASA_LARGE_CELLS(NCHP) large_cells_kernel<NCHP><<<ga, 256, 0, st>>>(kp, N, a0, w.hdr, w.sorted, w.orig, w.cells, w.bstart, w.val, range_rank, range_n, blk)
-            if (shift == 0) SASA_LARGE_CELLS(1);
-            else if (shift == 1) SASA_LARGE_CELLS(2);
-            else if (shift == 2) SASA_LARGE_CELLS(4);
+            if (kp.n_points <= 128) SASA_LARGE_CELLS(1);
             else SASA_LARGE_CELLS(8);
 #undef SASA_LARGE_CELLS
         } else {

@@ -15,6 +15,7 @@
 // headline configuration).  Template parameters: NT threads, MINB resident CTAs per SM, HAS_CLS (Atom.id
 // equality classes present).
 #pragma once
+#include "sasa_cap.cuh"
 #include "sasa_device.cuh"
 
 namespace sasa {
@@ -485,7 +486,13 @@ __global__ void __launch_bounds__(NT, MINB) sasa_small_kernel(const KParams p) {
                     k = cc.total >= 0 ? gather_cached(p, atoms, V.cls, pos, ai, cc, w_cand)
                                       : gather_candidates(p, g, atoms, V.cell, V.cls, pos, ai, w_cand);
                 }
-                if (k >= 0) {
+                if (k >= 0 && p.capm_in) {
+                    // 128 < n_points <= 1024: the chunked cap table (sasa_cap.cuh) on the shared-memory atoms; the entry strip
+                    // serves as the packed (bin, index) scratch
+                    cnt = capm_atom<8, 13>(p.capm_in, p.capm_rg, p.capd, atoms, ai, p.probe, w_cand, k, reinterpret_cast<uint32_t *>(w_ent),
+                                           p.pts4, (int)p.n_points, (int)min(p.n_points, p.n_body));
+                    pairs += (unsigned)k;
+                } else if (k >= 0) {
                     const float r = __fadd_rn(ai.w, p.probe);
                     const int nfront = build_entries(p, atoms, ai, __fmul_rn(r, r), __fmul_rn(2.0f, r), w_cand, k, w_ent);
                     cnt = (int)atom_fast(p, w_ent, k, nfront, w_cand, s_pts);

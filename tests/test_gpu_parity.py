@@ -503,6 +503,15 @@ def test_chunked_cap_table_randomised_geometry(eng, seed):
         if t == 2:   # 300 atoms inside a 5 A ball: > 128 neighbours each and > 288 candidates in the cell block
             xyz[100:400] = xyz[50] + rng.normal(scale=1.6, size=(300, 3))
         structs.append(np.concatenate([xyz, rad[:, None]], axis=1).astype(np.float32))
+    for t in range(5):   # structures of the fused kernels: the same table on shared-memory atoms (sasa_small_kernel)
+        n = int(rng.integers(40, 3000))
+        density = float(rng.choice([0.01, 0.057, 0.1]))
+        side = (n / density) ** (1.0 / 3.0)
+        xyz = rng.uniform(0.0, side, size=(n, 3)) + rng.uniform(-200, 200, size=3)
+        rad = rng.uniform(0.4, 3.2, size=n) if t % 2 else rng.choice([1.42, 1.61, 1.76, 1.88], size=n)
+        xyz[1] = xyz[0]
+        xyz[3] = xyz[2] + 1e-4
+        structs.append(np.concatenate([xyz, rad[:, None]], axis=1).astype(np.float32))
     off = np.cumsum([0] + [s.shape[0] for s in structs]).astype(np.uint64)
     xyzr = np.concatenate(structs)
     b = eng.batch(off)
