@@ -38,6 +38,9 @@
 #define SASA_CAP_R2 1          // rounds 0 and 1 (the first 64 neighbours) are fetched together: one OR-reduction for both, the
                                // ring tests of round 0 already see the inner masks of round 1, and both fetches overlap
 #endif
+#ifndef SASA_CAP_LAZYDIV
+#define SASA_CAP_LAZYDIV 0     // (measured: 560.6 -> 557.3 instructions per atom, +0.1 % -- the division still runs whenever any lane of the warp has a ring point; off) the IEEE division of the entry's limit (src/lib.rs:135-136) only in lanes that really run an exact
+#endif                         // test; the table lookup takes limit ~ numerator x rcp(2r), well inside the bins' margins
 #ifndef SASA_CAP_PF
 #define SASA_CAP_PF 0          // fetch the next round's masks before the current round's ring tests
 #endif
@@ -225,9 +228,15 @@ __device__ __forceinline__ bool cap_exact(const float4 *pts, int pt, const float
 
 // Exact tests of this lane's neighbour e against its ring points (m0..m3: points 0-31, .., 96-127 still uncovered);
 // points found occluded are OR-ed into a0..a3.
-__device__ __forceinline__ void cap_ring_tests(unsigned m0, unsigned m1, unsigned m2, unsigned m3, const float4 e,
+__device__ __forceinline__ void cap_ring_tests(unsigned m0, unsigned m1, unsigned m2, unsigned m3, float4 e, float two_r,
                                                const float4 *pts, int nbody, unsigned &a0, unsigned &a1, unsigned &a2,
                                                unsigned &a3) {
+#if SASA_CAP_LAZYDIV
+    // e.w still holds the numerator (t_j - |v|^2) - r^2: the reference's limit is its IEEE quotient by 2r
+    if ((m0 | m1 | m2 | m3) != 0u) e.w = __fdiv_rn(e.w, two_r);
+#else
+    (void)two_r;
+#endif
 #if SASA_CAP_RING1
     // every trip takes the highest point left in the lane's 128-bit mask; the warp runs max-over-lanes trips
     while (__any_sync(kFull, (m0 | m1 | m2 | m3) != 0u)) {
@@ -263,23 +272,42 @@ __device__ __forceinline__ void cap_ring_tests(unsigned m0, unsigned m1, unsigne
 }
 
 struct CapRound {
-    float4 e;       // this lane's neighbour: (vx, vy, vz, limit), the reference's arithmetic
+    float4 e;       // this lane's neighbour: (vx, vy, vz, limit), the reference's arithmetic (SASA_CAP_LAZYDIV: .w = the limit's
+                    // numerator; cap_ring_tests divides where a test is due)
     uint4 in, rg;   // its bin's inner and ring masks
 };
+
+// make_entry without the division: (vx, vy, vz, (t_j - |v|^2) - r^2), same operations in the same order (src/lib.rs:128-136).
+__device__ __forceinline__ float4 make_entry_num(const float4 ai, const float4 aj, float probe, float r2, float *vmag_out) {
+    const float vx = __fsub_rn(ai.x, aj.x), vy = __fsub_rn(ai.y, aj.y), vz = __fsub_rn(ai.z, aj.z);
+    const float vmag = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+    const float tj = __fadd_rn(aj.w, probe);
+    const float t = __fmul_rn(tj, tj);
+    *vmag_out = vmag;
+    return make_float4(vx, vy, vz, __fsub_rn(__fsub_rn(t, vmag), r2));
+}
 
 // Lane `lane` of the round starting at q0: entry + table fetch (lanes past k fetch the empty bin).
 // Atoms: accessor of the cell-sorted atoms (shared-memory array in the fused kernel, global array in the large-structure path);
 // IdxT: type of the candidate positions.
 template <class Atoms, class IdxT>
 __device__ __forceinline__ CapRound cap_fetch(const uint4 *__restrict__ tab, const Atoms &s_atom, const float4 ai, float probe,
-                                              float r2, float two_r, const IdxT *cand, int q, int k) {
+                                              float r2, float two_r, float inv_two_r, const IdxT *cand, int q, int k) {
     CapRound R;
     const bool valid = q < k;
     const float4 aj = s_atom(valid ? (int)cand[q] : 0);
     float vmag;
+#if SASA_CAP_LAZYDIV
+    R.e = make_entry_num(ai, aj, probe, r2, &vmag);
+    float4 eb = R.e;
+    eb.w = R.e.w * inv_two_r;   // approximate limit: good for the table lookup only
+#else
     R.e = make_entry(ai, aj, probe, r2, two_r, &vmag);
+    const float4 eb = R.e;
+    (void)inv_two_r;
+#endif
     // (nearly) coincident centres: no direction -- the degenerate bin sends every point to the exact test
-    const int bin = valid ? (vmag >= kCapMinV2 ? cap_bin(R.e, vmag) : (int)kCapBinDegenerate) : (int)kCapBinEmpty;
+    const int bin = valid ? (vmag >= kCapMinV2 ? cap_bin(eb, vmag) : (int)kCapBinDegenerate) : (int)kCapBinEmpty;
     const uint4 *b = tab + 2 * (size_t)(unsigned)bin;
 #if SASA_CAP_LD256
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -293,12 +321,12 @@ __device__ __forceinline__ CapRound cap_fetch(const uint4 *__restrict__ tab, con
 }
 
 // One round of an atom, given this lane's entry and masks: OR of the inner masks, exact tests of the ring points left.
-__device__ __forceinline__ void cap_round(const CapRound &R, const float4 *pts, int nbody, unsigned &a0, unsigned &a1, unsigned &a2,
-                                          unsigned &a3) {
+__device__ __forceinline__ void cap_round(const CapRound &R, float two_r, const float4 *pts, int nbody, unsigned &a0, unsigned &a1,
+                                          unsigned &a2, unsigned &a3) {
     a0 |= R.in.x; a1 |= R.in.y; a2 |= R.in.z; a3 |= R.in.w;
     const unsigned c0 = __reduce_or_sync(kFull, a0), c1 = __reduce_or_sync(kFull, a1),
                    c2 = __reduce_or_sync(kFull, a2), c3 = __reduce_or_sync(kFull, a3);
-    cap_ring_tests(R.rg.x & ~c0, R.rg.y & ~c1, R.rg.z & ~c2, R.rg.w & ~c3, R.e, pts, nbody, a0, a1, a2, a3);
+    cap_ring_tests(R.rg.x & ~c0, R.rg.y & ~c1, R.rg.z & ~c2, R.rg.w & ~c3, R.e, two_r, pts, nbody, a0, a1, a2, a3);
 }
 
 __device__ __forceinline__ int cap_covered(unsigned a0, unsigned a1, unsigned a2, unsigned a3) {
@@ -316,40 +344,41 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const Ato
     const int lane = lane_id();
     const float r = __fadd_rn(ai.w, probe);
     const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
+    const float inv_two_r = cap_rcp(two_r);
     unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;      // this lane's inner masks and exact hits, not yet reduced
 #if SASA_CAP_R2
     {
-        const CapRound A = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, lane, k);
+        const CapRound A = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, lane, k);
         CapRound B;
         B.e = make_float4(0.f, 0.f, 0.f, 0.f);
         B.in = make_uint4(0u, 0u, 0u, 0u);
         B.rg = B.in;
-        if (k > 32) B = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, 32 + lane, k);
+        if (k > 32) B = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, 32 + lane, k);
         a0 = A.in.x | B.in.x; a1 = A.in.y | B.in.y; a2 = A.in.z | B.in.z; a3 = A.in.w | B.in.w;
         const unsigned c0 = __reduce_or_sync(kFull, a0), c1 = __reduce_or_sync(kFull, a1),
                        c2 = __reduce_or_sync(kFull, a2), c3 = __reduce_or_sync(kFull, a3);
-        cap_ring_tests(A.rg.x & ~c0, A.rg.y & ~c1, A.rg.z & ~c2, A.rg.w & ~c3, A.e, pts, nbody, a0, a1, a2, a3);
-        if (k > 32) cap_ring_tests(B.rg.x & ~c0, B.rg.y & ~c1, B.rg.z & ~c2, B.rg.w & ~c3, B.e, pts, nbody, a0, a1, a2, a3);
+        cap_ring_tests(A.rg.x & ~c0, A.rg.y & ~c1, A.rg.z & ~c2, A.rg.w & ~c3, A.e, two_r, pts, nbody, a0, a1, a2, a3);
+        if (k > 32) cap_ring_tests(B.rg.x & ~c0, B.rg.y & ~c1, B.rg.z & ~c2, B.rg.w & ~c3, B.e, two_r, pts, nbody, a0, a1, a2, a3);
     }
 #pragma unroll 1
     for (int q0 = 64; q0 < k; q0 += 32) {
-        const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, q0 + lane, k);
-        cap_round(R, pts, nbody, a0, a1, a2, a3);
+        const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, q0 + lane, k);
+        cap_round(R, two_r, pts, nbody, a0, a1, a2, a3);
     }
 #elif SASA_CAP_PF
-    CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, lane, k);
+    CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, lane, k);
 #pragma unroll 1
     for (int q0 = 0; q0 < k; q0 += 32) {
         CapRound Nx = R;
-        if (q0 + 32 < k) Nx = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, q0 + 32 + lane, k);
-        cap_round(R, pts, nbody, a0, a1, a2, a3);
+        if (q0 + 32 < k) Nx = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, q0 + 32 + lane, k);
+        cap_round(R, two_r, pts, nbody, a0, a1, a2, a3);
         R = Nx;
     }
 #else
 #pragma unroll 1
     for (int q0 = 0; q0 < k; q0 += 32) {
-        const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, cand, q0 + lane, k);
-        cap_round(R, pts, nbody, a0, a1, a2, a3);
+        const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, q0 + lane, k);
+        cap_round(R, two_r, pts, nbody, a0, a1, a2, a3);
     }
 #endif
     return n_points - cap_covered(a0, a1, a2, a3);
