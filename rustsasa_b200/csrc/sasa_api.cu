@@ -216,7 +216,8 @@ struct Proto {
               sasa_tight_kernel<NT, MINB, false, CMAX, 0>, sasa_tight_kernel<NT, MINB, true, CMAX, 0>,                 \
               sasa_tight_kernel<NT, MINB, false, CMAX, 3>, sasa_tight_kernel<NT, MINB, true, CMAX, 3> } }
 // 0-2 keep 32 warps resident per SM (64 registers/thread); 3-4 keep 24 warps (85 registers/thread)
-#ifdef SASA_DEFAULT_PROTOS_ONLY   // quick builds of tuning variants: only the default configurations are instantiated
+#ifndef SASA_ALL_PROTOS   // the shipped build instantiates the two default configurations only (half the build time and library
+                         // size); -DSASA_ALL_PROTOS adds the three tuning configurations selectable with SASA_B200_CFGS
 #ifndef SASA_NT_MAIN
 #define SASA_NT_MAIN 1024
 #endif
@@ -1333,6 +1334,9 @@ static int single_run(sasa_b200_ctx *ctx, const float *xyzr, const uint32_t *cls
         const size_t want = o + o / 4 + (64 << 10);
         if ((e = cudaMalloc((void **)&sl->d_buf, want)) != cudaSuccess) return failed(SASA_B200_ERR_CUDA, "cudaMalloc", e);
         if ((e = cudaHostAlloc((void **)&sl->h_pin, want, cudaHostAllocDefault)) != cudaSuccess) return failed(SASA_B200_ERR_CUDA, "cudaHostAlloc", e);
+        // the sections of the layout are 256-byte aligned and travel in one copy each way: define the gaps once
+        memset(sl->h_pin, 0, want);
+        cudaMemset(sl->d_buf, 0, want);
         sl->d_bytes = sl->h_bytes = want;
     }
     if (N > sl->large.cap_atoms) {

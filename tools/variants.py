@@ -18,7 +18,7 @@ VDIR = os.path.join(ROOT, "rustsasa_b200", "variants")
 def one(spec):
     name, _, flags = spec.partition(":")
     out = os.path.join(VDIR, f"libsasa_b200_{name}.so")
-    B.build(force=True, defines=tuple(["-DSASA_DEFAULT_PROTOS_ONLY"] + flags.split()), out=out)
+    B.build(force=True, defines=tuple(flags.split()), out=out)
     return out
 
 
