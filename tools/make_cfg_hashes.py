@@ -34,6 +34,18 @@ def main():
                         xyzr_sha256=hashlib.sha256(np.ascontiguousarray(data.xyzr).tobytes()).hexdigest(),
                         oracle_seconds=round(time.perf_counter() - t0, 1))
         print(key, out[key], flush=True)
+    # cfg3: protein totals (global, polar, non-polar) of the frames a rank of an N = 1, 2, 4 or 8 job starts with
+    md = W.md_trajectory(n_frames=10000, n_atoms=5000)
+    frames = sorted({10000 * r // w for w in (1, 2, 4, 8) for r in range(w)})
+    tot = {}
+    for f in frames:
+        xyzr = np.concatenate([md.xyz[f], md.radii[:, None]], axis=1).astype(np.float32)
+        o = fast.calculate_sasa_internal(xyzr, 1.4, 100, threads=-1)
+        t = fast.protein_totals(o["sasa"], md.seg_be, md.seg_polar)
+        tot[str(f)] = [float(x) for x in np.asarray(t, np.float32)]
+    out["cfg3"] = dict(frames=10000, atoms_per_frame=int(md.xyz.shape[1]), n_points=100, protein_totals=tot,
+                       xyz_sha256_first_frame=hashlib.sha256(np.ascontiguousarray(md.xyz[0]).tobytes()).hexdigest())
+    print("cfg3", out["cfg3"], flush=True)
     with open(os.path.join(ROOT, "tests", "golden", "cfg_hashes.json"), "w") as fh:
         json.dump(out, fh, indent=1)
 
