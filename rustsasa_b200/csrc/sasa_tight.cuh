@@ -67,6 +67,14 @@ namespace sasa {
 #ifndef SASA_OPT_GRIDLD
 #define SASA_OPT_GRIDLD 0     // 1: the grid is re-read from shared memory at every cell instead of living in registers (-1 %)
 #endif
+#ifndef SASA_OPT_PAIR
+#define SASA_OPT_PAIR 1       // pairs of atoms of a cell share one pass over the cell's candidate list: each candidate is loaded once
+                              // and tested against both (VERDICT r01's per-cell gather in the form that paid).  Measured on cfg2
+                              // (gpurun_out r02w-r02z): off 1,635 M atoms/s / 560.6 warp instructions per atom; pairs 1,684 / 539.0;
+                              // groups of up to 3 or 4 atoms with the occlusion unrolled per atom 1,022 / 670 (three more copies of
+                              // cap_atom push the hot code out of the instruction cache: issue utilisation 49 % / 32 %); the same
+                              // groups with ONE rolled occlusion loop 1,523-1,591 (the bookkeeping costs more than the loads saved)
+#endif
 #ifndef SASA_OPT_NEXT
 #define SASA_OPT_NEXT 1       // warp 0 claims the CTA's next structure and prefetches its atoms into L2 while the other
                               // warps already work on the current one (hides the claim / first-touch latency of the setup)
@@ -195,6 +203,34 @@ __device__ __forceinline__ int tight_gather(const float4 *s_atom, const uint32_t
 #endif
     __syncwarp();
     return k;
+}
+
+// Two atoms of one cell against the listed candidates in ONE pass: every candidate is loaded once and tested against both.
+__device__ __forceinline__ void tight_gather2(const float4 *s_atom, const uint16_t *list, int total, int pos_a, int pos_b,
+                                              const float4 aa, const float4 ab, float reach_a, float reach_b, uint16_t *cand_a,
+                                              uint16_t *cand_b, int &ka, int &kb) {
+    const int lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    int k0 = 0, k1 = 0;
+#pragma unroll 1
+    for (int w0 = 0; w0 < total; w0 += 32) {
+        const int j = (int)list[w0 + lane];
+        const float4 b = s_atom[j];
+        const float dxa = aa.x - b.x, dya = aa.y - b.y, dza = aa.z - b.z;
+        const float dxb = ab.x - b.x, dyb = ab.y - b.y, dzb = ab.z - b.z;
+        const float d2a = fmaf(dxa, dxa, fmaf(dya, dya, dza * dza)), d2b = fmaf(dxb, dxb, fmaf(dyb, dyb, dzb * dzb));
+        const float ca = reach_a + b.w, cb = reach_b + b.w;
+        const bool acc_a = (d2a <= ca * ca) & (j != pos_a), acc_b = (d2b <= cb * cb) & (j != pos_b);   // sentinel pads fail both
+        const unsigned ma = __ballot_sync(kFull, acc_a), mb = __ballot_sync(kFull, acc_b);
+        const int at_a = k0 + __popc(ma & lt), at_b = k1 + __popc(mb & lt);
+        if (acc_a & (at_a < kQueueCap)) cand_a[at_a] = (uint16_t)j;
+        if (acc_b & (at_b < kQueueCap)) cand_b[at_b] = (uint16_t)j;
+        k0 += __popc(ma);
+        k1 += __popc(mb);
+    }
+    __syncwarp();
+    ka = k0;
+    kb = k1;
 }
 
 // (vx, vy, vz, limit) per neighbour -- the per-pair setup of src/lib.rs:128-136 -- with the "near" neighbours
@@ -473,6 +509,23 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                 const int cell_end = min((int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1], pos_end);
 #endif
                 const int total = tight_fill_list(g, V.cell, cx, cy, cz, w_list, N);
+#if SASA_OPT_PAIR && SASA_OPT_CAP
+                if (!HAS_CLS && total >= 0) {
+                    uint16_t *const w_cand2 = reinterpret_cast<uint16_t *>(w_ent);   // the entry strip is idle on the cap path
+                    while (pos + 1 < cell_end) {
+                        const float4 aa = V.atom[pos], ab = V.atom[pos + 1];
+                        int ka, kb;
+                        tight_gather2(V.atom, w_list, total, pos, pos + 1, aa, ab, aa.w + reach0, ab.w + reach0, w_cand, w_cand2, ka, kb);
+                        if (ka > kNbCap || kb > kNbCap) break;   // dense neighbourhood: the one-atom path below sorts it out
+                        const int ca = cap_atom(p.cap, SmemAtoms{V.atom}, aa, p.probe, w_cand, ka, V.ptab, (int)p.n_points, nbody);
+                        const int cb = cap_atom(p.cap, SmemAtoms{V.atom}, ab, p.probe, w_cand2, kb, V.ptab, (int)p.n_points, nbody);
+                        pairs += (unsigned)(ka + kb);
+                        if (lane < 2) V.val[(int)V.orig[pos + lane]] = (float)(lane ? cb : ca);
+                        __syncwarp();
+                        pos += 2;
+                    }
+                }
+#endif
                 for (; pos < cell_end; ++pos) {
                     const float4 ai = V.atom[pos];
                     int cnt;
