@@ -212,7 +212,11 @@ __device__ __forceinline__ void tight_gather2(const float4 *s_atom, const uint16
     const int lane = lane_id();
     const unsigned lt = lanemask_lt();
     int k0 = 0, k1 = 0;
-#pragma unroll 1
+#ifndef SASA_OPT_PAIR_U
+#define SASA_OPT_PAIR_U 1
+#endif
+    constexpr int kPairUnroll = SASA_OPT_PAIR_U;
+#pragma unroll kPairUnroll
     for (int w0 = 0; w0 < total; w0 += 32) {
         const int j = (int)list[w0 + lane];
         const float4 b = s_atom[j];
