@@ -41,6 +41,9 @@
 #ifndef SASA_CAP_LAZYDIV
 #define SASA_CAP_LAZYDIV 0     // (measured: 560.6 -> 557.3 instructions per atom, +0.1 % -- the division still runs whenever any lane of the warp has a ring point; off) the IEEE division of the entry's limit (src/lib.rs:135-136) only in lanes that really run an exact
 #endif                         // test; the table lookup takes limit ~ numerator x rcp(2r), well inside the bins' margins
+#ifndef SASA_CAP_FULLX
+#define SASA_CAP_FULLX 1       // 1: an atom whose points are ALL inside inner masks after the first reduction (42 % of the atoms of a
+#endif                         // protein) returns 0 there: no ring masks, no ring loops, no second reduction
 #ifndef SASA_CAP_PF
 #define SASA_CAP_PF 0          // fetch the next round's masks before the current round's ring tests
 #endif
@@ -357,6 +360,10 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const Ato
         a0 = A.in.x | B.in.x; a1 = A.in.y | B.in.y; a2 = A.in.z | B.in.z; a3 = A.in.w | B.in.w;
         const unsigned c0 = __reduce_or_sync(kFull, a0), c1 = __reduce_or_sync(kFull, a1),
                        c2 = __reduce_or_sync(kFull, a2), c3 = __reduce_or_sync(kFull, a3);
+#if SASA_CAP_FULLX
+        // the masks hold bits of existing points only, so full coverage is a population count
+        if (__popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) == n_points) return 0;
+#endif
         cap_ring_tests(A.rg.x & ~c0, A.rg.y & ~c1, A.rg.z & ~c2, A.rg.w & ~c3, A.e, two_r, pts, nbody, a0, a1, a2, a3);
         if (k > 32) cap_ring_tests(B.rg.x & ~c0, B.rg.y & ~c1, B.rg.z & ~c2, B.rg.w & ~c3, B.e, two_r, pts, nbody, a0, a1, a2, a3);
     }

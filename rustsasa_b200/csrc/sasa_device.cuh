@@ -79,7 +79,23 @@ struct Grid {
     int nx, ny, nz, e;
 };
 
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+#ifndef SASA_OPT_LANEID
+#define SASA_OPT_LANEID 0      // 1: the lane index from %laneid (one S2R) instead of threadIdx.x & 31 (S2R + LOP3) wherever ptxas
+#endif                        // rematerialises it -- measured: 6 instructions per atom fewer but 1 % slower (r04b: 1,848 vs 1,868), off
+__device__ __forceinline__ int lane_id() {
+#if SASA_OPT_LANEID
+    unsigned l;
+    asm("mov.u32 %0, %%laneid;" : "=r"(l));
+    return (int)l;
+#else
+    return threadIdx.x & 31;
+#endif
+}
+// A warp-uniform value routed through a warp reduction: REDUX writes a UNIFORM register, so ptxas may keep the value (and
+// what is computed from it) on the uniform datapath instead of in one of the 64 vector registers of every thread.
+__device__ __forceinline__ unsigned uniform_u32(unsigned v) { return __reduce_max_sync(kFull, v); }
+__device__ __forceinline__ int uniform_i32(int v) { return (int)__reduce_max_sync(kFull, (unsigned)v); }
+__device__ __forceinline__ float uniform_f32(float v) { return __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(v))); }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

@@ -75,6 +75,29 @@ namespace sasa {
                               // cap_atom push the hot code out of the instruction cache: issue utilisation 49 % / 32 %); the same
                               // groups with ONE rolled occlusion loop 1,523-1,591 (the bookkeeping costs more than the loads saved)
 #endif
+#ifndef SASA_OPT_UWARP
+#define SASA_OPT_UWARP 1      // 1: the warp index goes through a warp reduction (REDUX writes a uniform register), so that the per-warp
+#endif                        // scratch addresses live on the uniform datapath; ptxas otherwise re-derives them from SR_TID.X wherever
+                              // the 64 vector registers run out.  Measured together with SASA_OPT_UGRID (gpurun_out r04a/r04b, cfg2):
+                              // either one alone changes nothing, both together 539.0 -> 512 warp instructions per atom, and with
+                              // SASA_OPT_NOGUARD + SASA_CAP_FULLX 487.2 (1,683 -> 1,867 M atoms/s); the spills of the per-atom loop
+                              // (five LDL per cell) are gone
+#ifndef SASA_OPT_UGRID
+#define SASA_OPT_UGRID 1      // 1: the structure's cell grid (eight CTA-uniform values) is held in uniform registers
+#endif
+#ifndef SASA_OPT_UCLAIM
+#define SASA_OPT_UCLAIM 0     // 1: the claimed atom range and the list length come out of warp reductions (uniform registers) instead of
+                              // shuffles -- measured neutral (r04c: 1,868 vs 1,867), off
+#endif
+#ifndef SASA_OPT_USTRUCT
+#define SASA_OPT_USTRUCT 0    // 1: the structure's id, first atom and atom count in uniform registers -- measured neutral (1,859), off
+#endif
+#ifndef SASA_OPT_UCELL
+#define SASA_OPT_UCELL 0      // 1: the end of the cell's atom run in a uniform register -- one more REDUX per cell: 495 instructions, 1,848; off
+#endif
+#ifndef SASA_OPT_NOGUARD
+#define SASA_OPT_NOGUARD 1    // 1: the neighbour lists of the cap path live in the idle entry strip with room for every listed
+#endif                        // candidate, so the gather needs no capacity test on its stores
 #ifndef SASA_OPT_NEXT
 #define SASA_OPT_NEXT 1       // warp 0 claims the CTA's next structure and prefetches its atoms into L2 while the other
                               // warps already work on the current one (hides the claim / first-touch latency of the setup)
@@ -101,7 +124,11 @@ __device__ __forceinline__ int tight_fill_list(const Grid &g, const uint16_t *ce
         const int t = __shfl_up_sync(kFull, incl, d);
         if (lane >= d) incl += t;
     }
+#if SASA_OPT_UCLAIM
+    const int total = (int)__reduce_max_sync(kFull, (unsigned)incl);   // the inclusive scan is non-decreasing: lane 31 holds the maximum
+#else
     const int total = __shfl_sync(kFull, incl, 31);
+#endif
     if (total > kListCap) return -1;
     const int maxlen = __reduce_max_sync(kFull, len);
     // row expansion, four positions per trip (the longest row of a protein-density cell block holds ~13 atoms)
@@ -166,7 +193,7 @@ __device__ __forceinline__ int tight_gather(const float4 *s_atom, const uint32_t
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const int at = k + __popc(m[g] & lt);
-            if (acc[g] & (at < kQueueCap)) cand[at] = (uint16_t)j[g];
+            if (SASA_OPT_NOGUARD ? acc[g] : (acc[g] & (at < kQueueCap))) cand[at] = (uint16_t)j[g];
             k += __popc(m[g]);
         }
     }
@@ -181,7 +208,7 @@ __device__ __forceinline__ int tight_gather(const float4 *s_atom, const uint32_t
         if (HAS_CLS) acc = acc && (s_cls[j] != cls_i);
         const unsigned m = __ballot_sync(kFull, acc);
         const int at = k + __popc(m & lt);
-        if (acc & (at < kQueueCap)) cand[at] = (uint16_t)j;
+        if (SASA_OPT_NOGUARD ? acc : (acc & (at < kQueueCap))) cand[at] = (uint16_t)j;
         k += __popc(m);
     }
 #else
@@ -227,8 +254,8 @@ __device__ __forceinline__ void tight_gather2(const float4 *s_atom, const uint16
         const bool acc_a = (d2a <= ca * ca) & (j != pos_a), acc_b = (d2b <= cb * cb) & (j != pos_b);   // sentinel pads fail both
         const unsigned ma = __ballot_sync(kFull, acc_a), mb = __ballot_sync(kFull, acc_b);
         const int at_a = k0 + __popc(ma & lt), at_b = k1 + __popc(mb & lt);
-        if (acc_a & (at_a < kQueueCap)) cand_a[at_a] = (uint16_t)j;
-        if (acc_b & (at_b < kQueueCap)) cand_b[at_b] = (uint16_t)j;
+        if (SASA_OPT_NOGUARD ? acc_a : (acc_a & (at_a < kQueueCap))) cand_a[at_a] = (uint16_t)j;
+        if (SASA_OPT_NOGUARD ? acc_b : (acc_b & (at_b < kQueueCap))) cand_b[at_b] = (uint16_t)j;
         k0 += __popc(ma);
         k1 += __popc(mb);
     }
@@ -424,11 +451,22 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
     constexpr int NW = NT / 32;
     constexpr uint32_t NMAX = max_atoms(NT, MINB, CMAX, HAS_CLS);
     const SmemView V = smem_view<NT, HAS_CLS, NMAX, CMAX>(smem);
+#if SASA_OPT_UWARP
+    const int lane = lane_id(), warp = uniform_i32((int)(threadIdx.x >> 5));
+#else
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#endif
     unsigned char *const wblock = smem + kOffWarpBlocks + (size_t)warp * kWarpBlockBytes;
     float4 *const w_ent = reinterpret_cast<float4 *>(wblock);
     uint16_t *const w_cand = reinterpret_cast<uint16_t *>(wblock + kWarpOffCand);
     uint16_t *const w_list = reinterpret_cast<uint16_t *>(wblock + kWarpOffList);
+#if SASA_OPT_NOGUARD && SASA_OPT_CAP
+    // neighbour lists of the cap path: two strips of kListCap positions inside the (idle) entry strip
+    static_assert(2 * (size_t)kListCap * 2 <= (size_t)kNbCap * 16, "entry strip too small for two full candidate lists");
+    uint16_t *const w_nba = reinterpret_cast<uint16_t *>(wblock), *const w_nbb = w_nba + kListCap;
+#else
+    uint16_t *const w_nba = w_cand, *const w_nbb = reinterpret_cast<uint16_t *>(w_ent);
+#endif
     stage_points(p, V.ptab);
     const int nbody = (int)min(p.n_points, p.n_body), nsl = (nbody + 31) >> 5;
     (void)nsl;
@@ -451,6 +489,14 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
         if (warp == 0) claim_next_and_prefetch(p, V.misc);   // every structure, also after a rejected one
 #endif
         if (!ok) continue;
+#if SASA_OPT_USTRUCT
+        sid = uniform_u32(sid); a0 = uniform_u32(a0); N = uniform_i32(N);
+#endif
+#if SASA_OPT_UGRID
+        g0.minx = uniform_f32(g0.minx); g0.miny = uniform_f32(g0.miny); g0.minz = uniform_f32(g0.minz);
+        g0.inv_c = uniform_f32(g0.inv_c);
+        g0.nx = uniform_i32(g0.nx); g0.ny = uniform_i32(g0.ny); g0.nz = uniform_i32(g0.nz); g0.e = uniform_i32(g0.e);
+#endif
 
         // ---- per-atom work: warps claim runs of the cell-sorted atom order, whole cells at a time; the atoms of a cell
         // share its candidate list ----
@@ -465,8 +511,13 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                 take = max(SASA_OPT_ACLAIM, min(16 * SASA_OPT_ACLAIM, left / (4 * NW)));
                 c0 = atomicAdd(&V.misc[1], take);
             }
+#if SASA_OPT_UCLAIM
+            c0 = uniform_i32(c0);       // lanes 1..31 hold 0
+            take = uniform_i32(take);
+#else
             c0 = __shfl_sync(kFull, c0, 0);
             take = __shfl_sync(kFull, take, 0);
+#endif
             if (c0 >= N) break;
             int pos = c0;
             const int pos_end = min(c0 + take, N);
@@ -507,7 +558,9 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                 const float4 a_first = V.atom[pos];
                 const int cx = cell_coord(a_first.x, g.minx, g.inv_c, g.nx), cy = cell_coord(a_first.y, g.miny, g.inv_c, g.ny),
                           cz = cell_coord(a_first.z, g.minz, g.inv_c, g.nz);
-#if SASA_OPT_ACLAIM > 0 && SASA_OPT_SNAP
+#if SASA_OPT_ACLAIM > 0 && SASA_OPT_SNAP && SASA_OPT_UCELL
+                const int cell_end = uniform_i32((int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1]);
+#elif SASA_OPT_ACLAIM > 0 && SASA_OPT_SNAP
                 const int cell_end = (int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1];   // whole cells, past pos_end if need be
 #else
                 const int cell_end = min((int)V.cell[(cz * g.ny + cy) * g.nx + cx + 1], pos_end);
@@ -515,7 +568,8 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                 const int total = tight_fill_list(g, V.cell, cx, cy, cz, w_list, N);
 #if SASA_OPT_PAIR && SASA_OPT_CAP
                 if (!HAS_CLS && total >= 0) {
-                    uint16_t *const w_cand2 = reinterpret_cast<uint16_t *>(w_ent);   // the entry strip is idle on the cap path
+                    uint16_t *const w_cand2 = w_nbb;   // the entry strip is idle on the cap path
+                    uint16_t *const w_cand = w_nba;
                     while (pos + 1 < cell_end) {
                         const float4 aa = V.atom[pos], ab = V.atom[pos + 1];
                         int ka, kb;
@@ -533,15 +587,20 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                 for (; pos < cell_end; ++pos) {
                     const float4 ai = V.atom[pos];
                     int cnt;
-                    int k = total >= 0 ? tight_gather<HAS_CLS>(V.atom, V.cls, w_list, total, pos, ai, ai.w + reach0, w_cand)
+#if SASA_OPT_CAP
+                    uint16_t *const w_nb = w_nba;
+#else
+                    uint16_t *const w_nb = w_cand;
+#endif
+                    int k = total >= 0 ? tight_gather<HAS_CLS>(V.atom, V.cls, w_list, total, pos, ai, ai.w + reach0, w_nb)
                                        : kNbCap + 1;
                     if (k <= kNbCap) {
 #if SASA_OPT_CAP
-                        cnt = cap_atom(p.cap, SmemAtoms{V.atom}, ai, p.probe, w_cand, k, V.ptab, (int)p.n_points, nbody);
+                        cnt = cap_atom(p.cap, SmemAtoms{V.atom}, ai, p.probe, w_nb, k, V.ptab, (int)p.n_points, nbody);
 #else
                         const float r = __fadd_rn(ai.w, p.probe);
                         const int nfront = tight_entries(V.atom, ai, p.probe, __fmul_rn(r, r), __fmul_rn(2.0f, r), p.near2,
-                                                         w_cand, k, w_ent);
+                                                         w_nb, k, w_ent);
                         if (NSLT > 0) cnt = tight_atom<NSLT ? NSLT : 1>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
                         else if (nsl == 3) cnt = tight_atom<3>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
                         else if (nsl == 4) cnt = tight_atom<4>(p, w_ent, k, nfront, V.ptab, w_cand, nbody, tail_sh);
