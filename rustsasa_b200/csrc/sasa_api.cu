@@ -177,7 +177,7 @@ int get_points(sasa_b200_ctx *ctx, uint32_t n, const Points **out) {
                 const int v = e ? atoi(e) : 64;
                 return v >= 8 && v <= 256 && v % 2 == 0 ? v : 64;
             }();
-            P.capd = cap_dims(grid_n, kCapL, 8);   // always eight chunk slots: capm_atom<8> serves every 128 < n <= 1024
+            P.capd = cap_dims(grid_n, kCapmL, 8);   // always eight chunk slots: capm_atom<8> serves every 128 < n <= 1024
             const size_t words = cap_multi_words(P.capd);
             std::vector<uint32_t> tin(words), trg(words);
             cap_build_table_multi(n, h.data(), h.data() + n, h.data() + 2 * (size_t)n, P.capd, tin.data(), trg.data());

@@ -26,7 +26,10 @@
 #define SASA_CAP_N 128         // direction bins per axis of the octahedral square (even)
 #endif
 #ifndef SASA_CAP_L
-#define SASA_CAP_L 64          // level bins over c in [-1, 1]
+#define SASA_CAP_L 128         // level bins over c in [-1, 1].  Thinner rings mean fewer exact tests: 64 -> 96 -> 128 levels gave
+                               // 1,916 -> 1,938 -> 1,946 M atoms/s (477.5 -> 470.6 -> 466.5 instructions per atom) for a 34.6 -> 51 -> 68 MB
+                               // table that still sits in the 126 MB L2 (gpurun_out r04f / r04g); 96 x 96 directions x 128 / 192 levels
+                               // (38 / 57 MB) measured slower than 128 x 128 x 128
 #endif
 #ifndef SASA_CAP_RING1
 #define SASA_CAP_RING1 1       // ring tests: one loop over the lane's whole 128-bit mask (0: one loop per 32-point word)
@@ -44,6 +47,9 @@
 #ifndef SASA_CAP_FULLX
 #define SASA_CAP_FULLX 1       // 1: an atom whose points are ALL inside inner masks after the first reduction (42 % of the atoms of a
 #endif                         // protein) returns 0 there: no ring masks, no ring loops, no second reduction
+#ifndef SASA_CAP_NOBR
+#define SASA_CAP_NOBR 1        // 1: cap_fetch computes the bin in every lane and selects the special bins instead of branching around
+#endif                         // the arithmetic: 477.5 -> 464.3 warp instructions per atom, 1,916 -> 1,958 M atoms/s (gpurun_out r04g)
 #ifndef SASA_CAP_PF
 #define SASA_CAP_PF 0          // fetch the next round's masks before the current round's ring tests
 #endif
@@ -51,6 +57,7 @@
 namespace sasa {
 
 constexpr int kCapN = SASA_CAP_N, kCapL = SASA_CAP_L;
+constexpr int kCapmL = 64;                                   // level bins of the chunked tables (128 < n <= 1024): 2 x 34.6 MB at 64 x 64 directions
 constexpr int kCapLevels = kCapL + 2;                       // level 0: c < -1, level L + 1: c >= 1
 constexpr size_t kCapBins = (size_t)kCapLevels * kCapN * kCapN;
 constexpr size_t kCapBinDegenerate = kCapBins;               // extra bin: no inner points, every point in the ring
@@ -310,7 +317,15 @@ __device__ __forceinline__ CapRound cap_fetch(const uint4 *__restrict__ tab, con
     (void)inv_two_r;
 #endif
     // (nearly) coincident centres: no direction -- the degenerate bin sends every point to the exact test
+#if SASA_CAP_NOBR
+    // branch-free: the bin arithmetic runs in every lane (it cannot trap: rsqrt(0) = inf, float -> int conversions saturate) and
+    // two selects pick the special bins
+    int bin = cap_bin(eb, vmag);
+    bin = vmag >= kCapMinV2 ? bin : (int)kCapBinDegenerate;
+    bin = valid ? bin : (int)kCapBinEmpty;
+#else
     const int bin = valid ? (vmag >= kCapMinV2 ? cap_bin(eb, vmag) : (int)kCapBinDegenerate) : (int)kCapBinEmpty;
+#endif
     const uint4 *b = tab + 2 * (size_t)(unsigned)bin;
 #if SASA_CAP_LD256
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

@@ -410,6 +410,9 @@ __device__ __noinline__ float large_cold_atom(const KParams &p, const Grid &g, c
     return atom_streaming<GlobalAtoms, uint32_t, false>(p, g, atoms, cells, nullptr, pos, ent, nullptr);
 }
 
+#ifndef SASA_OPT_ULARGE
+#define SASA_OPT_ULARGE 1
+#endif
 template <int NCHP>
 __global__ void __launch_bounds__(256, 4) large_cells_kernel(const KParams p, int N, uint32_t a0, LargeHeader *h,
                                                              const float4 *__restrict__ sorted, const uint32_t *__restrict__ orig,
@@ -424,8 +427,17 @@ __global__ void __launch_bounds__(256, 4) large_cells_kernel(const KParams p, in
         large_blank_outputs(p, N, a0);
         return;
     }
-    const Grid g = h->grid;
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    // the grid and the warp index on the uniform datapath (see SASA_OPT_UWARP / SASA_OPT_UGRID in sasa_tight.cuh).  Measured
+    // (gpurun_out r04e): cfg4 (NCHP = 1) 0.1875 -> 0.1854 ms, cfg5 (NCHP = 8) 1.65 -> 2.00 ms -- the chunked cap path has no
+    // vector registers to spare for the extra moves -- so only the 100-point instance takes it
+    Grid g = h->grid;
+    const int lane = lane_id();
+    int warp = threadIdx.x >> 5;
+    if (SASA_OPT_ULARGE && NCHP == 1) {
+        g.minx = uniform_f32(g.minx); g.miny = uniform_f32(g.miny); g.minz = uniform_f32(g.minz); g.inv_c = uniform_f32(g.inv_c);
+        g.nx = uniform_i32(g.nx); g.ny = uniform_i32(g.ny); g.nz = uniform_i32(g.nz); g.e = uniform_i32(g.e);
+        warp = uniform_i32(warp);
+    }
     float4 *const st = s_stage[warp];
     uint16_t *const nb = s_nb[warp];
     const int nbody = (int)min(p.n_points, p.n_body);

@@ -33,6 +33,15 @@ namespace sasa {
 #ifndef SASA_OPT_FILL4
 #define SASA_OPT_FILL4 1      // fill_list: four positions per trip
 #endif
+#ifndef SASA_OPT_FILLP
+#define SASA_OPT_FILLP 1      // fill_list: the four stores of a trip predicated (inline PTX) instead of branched: 487.2 -> 477.5 warp
+                              // instructions per atom, 1,863 -> 1,912 M atoms/s (gpurun_out r04f)
+#endif
+#ifndef SASA_OPT_HDR
+#define SASA_OPT_HDR 1        // fill_list header: lane / w by multiplication (nvcc emitted the 30-instruction integer division per claim),
+                              // inclusive scan with the shuffle's own predicate on the add: 454.0 -> 449.1 warp instructions per atom,
+                              // 1,986 -> 2,012 M atoms/s (gpurun_out r04h)
+#endif
 #ifndef SASA_OPT_P1U
 #define SASA_OPT_P1U 4        // phase 1: entries per unrolled trip
 #endif
@@ -109,7 +118,13 @@ __device__ __forceinline__ int tight_fill_list(const Grid &g, const uint16_t *ce
                                                uint16_t *list, int sentinel) {
     const int lane = lane_id();
     const int w = 2 * g.e + 1;
+#if SASA_OPT_HDR
+    // lane / w without the integer-division sequence: the search extent e is 1 or 2, so w is 3 or 5 (exact for lane < 32)
+    const int q = g.e == 2 ? (lane * 13) >> 6 : (lane * 11) >> 5;
+    const int dy = lane - q * w - g.e, dz = q - g.e;
+#else
     const int dy = lane % w - g.e, dz = lane / w - g.e;
+#endif
     const int y = cy + dy, z = cz + dz;
     int start = 0, len = 0;
     if (lane < w * w && y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
@@ -119,11 +134,19 @@ __device__ __forceinline__ int tight_fill_list(const Grid &g, const uint16_t *ce
         len = (int)cell[base + x1 + 1] - start;
     }
     int incl = len;
+#if SASA_OPT_HDR
+    // inclusive scan, two instructions per step: the shuffle's own predicate (source lane in range) guards the addition
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+        asm volatile("{\n .reg .pred p;\n .reg .b32 t;\n shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n @p add.s32 %0, %0, t;\n}"
+                     : "+r"(incl) : "r"(d));
+#else
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int t = __shfl_up_sync(kFull, incl, d);
         if (lane >= d) incl += t;
     }
+#endif
 #if SASA_OPT_UCLAIM
     const int total = (int)__reduce_max_sync(kFull, (unsigned)incl);   // the inclusive scan is non-decreasing: lane 31 holds the maximum
 #else
@@ -132,7 +155,24 @@ __device__ __forceinline__ int tight_fill_list(const Grid &g, const uint16_t *ce
     if (total > kListCap) return -1;
     const int maxlen = __reduce_max_sync(kFull, len);
     // row expansion, four positions per trip (the longest row of a protein-density cell block holds ~13 atoms)
-#if SASA_OPT_FILL4
+#if SASA_OPT_FILLP
+    // the same with four PREDICATED stores per trip (nvcc turns the monotone conditions below into a chain of divergent
+    // branches: 22 instructions per trip with a reconvergence point; this form is 15)
+    uint32_t dsts = (uint32_t)__cvta_generic_to_shared(list + (incl - len));
+    int v = start, left = len;
+#pragma unroll 1
+    for (int t = 0; t < maxlen; t += 4) {
+        asm volatile("{\n .reg .pred p0, p1, p2, p3;\n"
+                     " setp.gt.s32 p0, %2, 0;\n setp.gt.s32 p1, %2, 1;\n setp.gt.s32 p2, %2, 2;\n setp.gt.s32 p3, %2, 3;\n"
+                     " @p0 st.shared.u16 [%0], %1;\n"
+                     " @p1 st.shared.u16 [%0+2], %3;\n"
+                     " @p2 st.shared.u16 [%0+4], %4;\n"
+                     " @p3 st.shared.u16 [%0+6], %5;\n}"
+                     :: "r"(dsts), "h"((uint16_t)v), "r"(left), "h"((uint16_t)(v + 1)), "h"((uint16_t)(v + 2)), "h"((uint16_t)(v + 3))
+                     : "memory");
+        dsts += 8; v += 4; left -= 4;
+    }
+#elif SASA_OPT_FILL4
     uint16_t *dst = list + (incl - len);
     int v = start, left = len;
 #pragma unroll 1
