@@ -42,14 +42,21 @@
                                // ring tests of round 0 already see the inner masks of round 1, and both fetches overlap
 #endif
 #ifndef SASA_CAP_LAZYDIV
-#define SASA_CAP_LAZYDIV 0     // (measured: 560.6 -> 557.3 instructions per atom, +0.1 % -- the division still runs whenever any lane of the warp has a ring point; off) the IEEE division of the entry's limit (src/lib.rs:135-136) only in lanes that really run an exact
-#endif                         // test; the table lookup takes limit ~ numerator x rcp(2r), well inside the bins' margins
+#define SASA_CAP_LAZYDIV 1     // the IEEE division of the entry's limit (src/lib.rs:135-136) only in lanes that really run an exact test; the
+#endif                         // table lookup takes limit ~ numerator x rcp(2r), well inside the bins' margins.  Round 1: 560.6 -> 557.3
+                               // instructions per atom, +0.1 % (off).  With the 128-level table fewer warps reach a ring test at all:
+                               // 448.0 -> 441.1 instructions per atom, 2,019 -> 2,029 M atoms/s (gpurun_out r04k); on
 #ifndef SASA_CAP_FULLX
-#define SASA_CAP_FULLX 1       // 1: an atom whose points are ALL inside inner masks after the first reduction (42 % of the atoms of a
-#endif                         // protein) returns 0 there: no ring masks, no ring loops, no second reduction
+#define SASA_CAP_FULLX 2       // 1: an atom whose points are ALL inside inner masks after the first reduction (42 % of the atoms of a
+#endif                         // protein) returns 0 there: no ring masks, no ring loops, no second reduction; 2: the same test as three
+                               // logic instructions for n_points > 96 instead of four population counts (+0.6 %, r04k)
 #ifndef SASA_CAP_NOBR
 #define SASA_CAP_NOBR 1        // 1: cap_fetch computes the bin in every lane and selects the special bins instead of branching around
 #endif                         // the arithmetic: 477.5 -> 464.3 warp instructions per atom, 1,916 -> 1,958 M atoms/s (gpurun_out r04g)
+// Tried and dropped (gpurun_out r04j): the entry's IEEE division as an explicit three-FFMA sequence with the reciprocal of 2r
+// refined once per atom and no FCHK range check (bit-identical to __fdiv_rn on a 2.6 M-operand self-test over 0.02 <= 2r <= 4096):
+// 449.1 -> 448.0 warp instructions per atom, no change in time -- __fdiv_rn's fast path already is that sequence plus three
+// instructions, and the range guard costs as many.
 #ifndef SASA_CAP_PF
 #define SASA_CAP_PF 0          // fetch the next round's masks before the current round's ring tests
 #endif
@@ -377,7 +384,14 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const Ato
                        c2 = __reduce_or_sync(kFull, a2), c3 = __reduce_or_sync(kFull, a3);
 #if SASA_CAP_FULLX
         // the masks hold bits of existing points only, so full coverage is a population count
+#if SASA_CAP_FULLX == 2
+        // more than 96 points: words 0-2 must be full and word 3 must hold its n - 96 low bits (three instructions instead of seven)
+        if (n_points > 96 ? ((c0 & c1 & c2) == 0xffffffffu && c3 == (0xffffffffu >> (128 - n_points)))
+                          : (__popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) == n_points))
+            return 0;
+#else
         if (__popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) == n_points) return 0;
+#endif
 #endif
         cap_ring_tests(A.rg.x & ~c0, A.rg.y & ~c1, A.rg.z & ~c2, A.rg.w & ~c3, A.e, two_r, pts, nbody, a0, a1, a2, a3);
         if (k > 32) cap_ring_tests(B.rg.x & ~c0, B.rg.y & ~c1, B.rg.z & ~c2, B.rg.w & ~c3, B.e, two_r, pts, nbody, a0, a1, a2, a3);
