@@ -293,6 +293,10 @@ __device__ __forceinline__ void large_blank_outputs(const KParams &p, int N, uin
 // profiles/r02a_cfg4_large_atoms.txt), compacts the neighbours into an index list and hands it to the cap-table
 // occlusion: cap_atom for n_points <= 128, capm_atom (chunked table) above.
 // ---------------------------------------------------------------------------------------------------------------------
+#ifndef SASA_OPT_LHDR
+#define SASA_OPT_LHDR 1       // large_stage / large_gather: division-free row header, predicated scan and position stores, neighbour list
+#endif                        // without capacity tests (as SASA_OPT_HDR / FILLP / NOGUARD of the fused kernel): cfg4 0.187 -> 0.185 ms,
+                              // cfg5 1.648 -> 1.614 ms (gpurun_out r04l)
 constexpr int kLCap = 288;    // staged candidates per cell block (largest seen at protein density: 266)
 constexpr int kLNb = 128;     // neighbours per atom on the fast path (protein lists peak around 75)
 
@@ -307,7 +311,13 @@ __device__ __forceinline__ int large_stage(const Grid &g, const uint32_t *__rest
                                            int cx, int cy, int cz, float4 *st, int &self0) {
     const int lane = lane_id();
     const int w = 2 * g.e + 1;
+#if SASA_OPT_LHDR
+    // as in tight_fill_list (SASA_OPT_HDR): lane / w by multiplication (w is 3 or 5), scan with the shuffle's own predicate
+    const int q = g.e == 2 ? (lane * 13) >> 6 : (lane * 11) >> 5;
+    const int dy = lane - q * w - g.e, dz = q - g.e;
+#else
     const int dy = lane % w - g.e, dz = lane / w - g.e;
+#endif
     const int y = cy + dy, z = cz + dz;
     int start = 0, len = 0;
     if (lane < w * w && y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
@@ -317,11 +327,18 @@ __device__ __forceinline__ int large_stage(const Grid &g, const uint32_t *__rest
         len = (int)__ldg(cells + base + x1 + 1) - start;
     }
     int incl = len;
+#if SASA_OPT_LHDR
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+        asm volatile("{\n .reg .pred p;\n .reg .b32 t;\n shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n @p add.s32 %0, %0, t;\n}"
+                     : "+r"(incl) : "r"(d));
+#else
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int t = __shfl_up_sync(kFull, incl, d);
         if (lane >= d) incl += t;
     }
+#endif
     const int total = __shfl_sync(kFull, incl, 31);
     // the cell's own row is lane e * w + e; its atoms sit (first atom of the cell - row start) into that row
     const int self_lane = g.e * w + g.e;
@@ -330,6 +347,23 @@ __device__ __forceinline__ int large_stage(const Grid &g, const uint32_t *__rest
     if (total > kLCap) return -1;
     const int maxlen = __reduce_max_sync(kFull, len);
     // positions first (parked in the .x slot of the destination), then one coalesced-by-row copy of the atoms themselves
+#if SASA_OPT_LHDR
+    {
+        uint32_t dsts = (uint32_t)__cvta_generic_to_shared(st + (incl - len));
+        int v = start, left = len;
+#pragma unroll 1
+        for (int t = 0; t < maxlen; t += 4) {
+            asm volatile("{\n .reg .pred p0, p1, p2, p3;\n"
+                         " setp.gt.s32 p0, %2, 0;\n setp.gt.s32 p1, %2, 1;\n setp.gt.s32 p2, %2, 2;\n setp.gt.s32 p3, %2, 3;\n"
+                         " @p0 st.shared.b32 [%0], %1;\n"
+                         " @p1 st.shared.b32 [%0+16], %3;\n"
+                         " @p2 st.shared.b32 [%0+32], %4;\n"
+                         " @p3 st.shared.b32 [%0+48], %5;\n}"
+                         :: "r"(dsts), "r"(v), "r"(left), "r"(v + 1), "r"(v + 2), "r"(v + 3) : "memory");
+            dsts += 64; v += 4; left -= 4;
+        }
+    }
+#else
     {
         int *dst = reinterpret_cast<int *>(st + (incl - len));
         int v = start, left = len;
@@ -342,6 +376,7 @@ __device__ __forceinline__ int large_stage(const Grid &g, const uint32_t *__rest
             dst += 16; v += 4; left -= 4;
         }
     }
+#endif
     __syncwarp();
     const int padded = (total + 31) & ~31;
 #pragma unroll 2
@@ -371,10 +406,10 @@ __device__ __forceinline__ int large_gather(const float4 *st, int total, int sel
         const bool acc0 = (d0 <= c0 * c0) & (w0 + lane != self), acc1 = (d1 <= c1 * c1) & (w0 + 32 + lane != self);
         const unsigned m0 = __ballot_sync(kFull, acc0), m1 = __ballot_sync(kFull, acc1);
         const int at0 = k + __popc(m0 & lt);
-        if (acc0 & (at0 < kLNb)) nb[at0] = (uint16_t)(w0 + lane);
+        if (SASA_OPT_LHDR ? acc0 : (acc0 & (at0 < kLNb))) nb[at0] = (uint16_t)(w0 + lane);
         k += __popc(m0);
         const int at1 = k + __popc(m1 & lt);
-        if (acc1 & (at1 < kLNb)) nb[at1] = (uint16_t)(w0 + 32 + lane);
+        if (SASA_OPT_LHDR ? acc1 : (acc1 & (at1 < kLNb))) nb[at1] = (uint16_t)(w0 + 32 + lane);
         k += __popc(m1);
     }
     if (w0 < total) {
@@ -385,7 +420,7 @@ __device__ __forceinline__ int large_gather(const float4 *st, int total, int sel
         const bool acc0 = (d0 <= c0 * c0) & (w0 + lane != self);
         const unsigned m0 = __ballot_sync(kFull, acc0);
         const int at0 = k + __popc(m0 & lt);
-        if (acc0 & (at0 < kLNb)) nb[at0] = (uint16_t)(w0 + lane);
+        if (SASA_OPT_LHDR ? acc0 : (acc0 & (at0 < kLNb))) nb[at0] = (uint16_t)(w0 + lane);
         k += __popc(m0);
     }
     __syncwarp();
@@ -421,7 +456,7 @@ __global__ void __launch_bounds__(256, 4) large_cells_kernel(const KParams p, in
     static_assert(kLCap * 16 >= kNbCap * 16 + kNbCap * 4 + 64, "the cold path's scratch must fit the staging strip");
     __shared__ __align__(16) float4 s_stage[8][kLCap];
     __shared__ __align__(16) uint32_t s_nbp[8][kLNb];
-    __shared__ __align__(16) uint16_t s_nb[8][kLNb];
+    __shared__ __align__(16) uint16_t s_nb[8][SASA_OPT_LHDR ? kLCap : kLNb];   // SASA_OPT_LHDR: room for every staged candidate, no capacity test in the gather
     __shared__ __align__(16) float4 s_ptab[NCHP == 1 ? 128 : 1];
     if (h->ncell == 0) {
         large_blank_outputs(p, N, a0);

@@ -2,7 +2,7 @@
 """Experiment: the same proteome batch, clipped so that every structure fits the 512-thread x 2-CTA/SM configuration,
 run device-resident under different SASA_B200_CFGS settings (which shared-memory configuration the structures land in).
 
-usage (GPU box): exp_cfg.py [hi_atoms] [cfgs ...]        e.g. exp_cfg.py 2590 12 2 1
+usage (GPU box): [EXP_MEAN_ATOMS=800 EXP_STRUCTURES=12000] exp_cfg.py [hi_atoms] [cfgs ...]        e.g. exp_cfg.py 2590 12 2 1
 """
 import os
 import sys
@@ -18,7 +18,9 @@ from rustsasa_b200 import workloads as W  # noqa: E402
 
 hi = int(sys.argv[1]) if len(sys.argv) > 1 else 2590
 cfgs = sys.argv[2:] or ["12", "2"]
-data = W.proteome_batch(4400, seed=W.SEED, hi=hi)
+mean = float(os.environ.get("EXP_MEAN_ATOMS", "2400"))
+nstruct = int(os.environ.get("EXP_STRUCTURES", "4400"))
+data = W.proteome_batch(nstruct, seed=W.SEED, hi=hi, mean_atoms=mean, sd_atoms=mean / 6.0, lo=min(400, int(mean / 2)))
 N, G = data.n_atoms, int(data.seg_be.shape[0])
 d_xyzr = torch.from_numpy(data.xyzr).cuda()
 ref = None
