@@ -39,6 +39,7 @@ thread_local std::string g_create_error;
 struct Points {
     float *d = nullptr;    // 3*n floats: x[n] y[n] z[n]
     uint4 *cap = nullptr;  // cap table (sasa_cap.cuh), n <= 128 only
+    cudaTextureObject_t cap_tex = 0;   // the same table as a linear uint4 texture (SASA_CAP_TEX)
     // 128 < n <= 1024: the points as float4 and the chunked cap table (inner / ring masks in separate arrays)
     float4 *d4 = nullptr;
     uint4 *capm_in = nullptr, *capm_rg = nullptr;
@@ -171,6 +172,18 @@ int get_points(sasa_b200_ctx *ctx, uint32_t n, const Points **out) {
             cap_build_table(n, h.data(), h.data() + n, h.data() + 2 * (size_t)n, t.data());
             CU_TRY(ctx, cudaMalloc(&P.cap, t.size() * sizeof(uint32_t)));
             CU_TRY(ctx, cudaMemcpy(P.cap, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+#if SASA_CAP_TEX
+            {
+                cudaResourceDesc rd = {};
+                rd.resType = cudaResourceTypeLinear;
+                rd.res.linear.devPtr = P.cap;
+                rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+                rd.res.linear.sizeInBytes = t.size() * sizeof(uint32_t);
+                cudaTextureDesc td = {};
+                td.readMode = cudaReadModeElementType;
+                CU_TRY(ctx, cudaCreateTextureObject(&P.cap_tex, &rd, &td, nullptr));
+            }
+#endif
         } else if (n <= 1024) {   // chunked table for the large-structure path (sasa_cap.cuh, capm_atom)
             static const int grid_n = [] {
                 const char *e = getenv("SASA_B200_CAPM_N");   // tuning aid: direction bins per axis (even)
@@ -410,6 +423,7 @@ struct RunArgs {
 void fill_run_params(KParams *kp, const Points *pts, const sasa_b200_params &prm) {
     const uint32_t n = prm.n_points;
     kp->cap = pts->cap;
+    kp->cap_tex = (unsigned long long)pts->cap_tex;
     kp->capm_in = pts->capm_in;
     kp->capm_rg = pts->capm_rg;
     kp->pts4 = pts->d4;
@@ -637,6 +651,7 @@ void sasa_b200_destroy(sasa_b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto &kv : ctx->points) {
+        if (kv.second.cap_tex) cudaDestroyTextureObject(kv.second.cap_tex);
         cudaFree(kv.second.d); cudaFree(kv.second.cap); cudaFree(kv.second.d4); cudaFree(kv.second.capm_in); cudaFree(kv.second.capm_rg);
     }
     for (int i = 0; i < kStreams; ++i)

@@ -57,6 +57,16 @@
 // refined once per atom and no FCHK range check (bit-identical to __fdiv_rn on a 2.6 M-operand self-test over 0.02 <= 2r <= 4096):
 // 449.1 -> 448.0 warp instructions per atom, no change in time -- __fdiv_rn's fast path already is that sequence plus three
 // instructions, and the range guard costs as many.
+#ifndef SASA_CAP_TEX
+#define SASA_CAP_TEX 1         // 1: the fused kernel reads the table through the TEXTURE path (two tex1Dfetch<uint4> per bin) instead of one
+#endif                         // LDG.E.256.  Once the instruction count was down to 441 per atom the LSU data pipe of L1TEX had become the
+                               // top unit (81 % busy: 74 shared-memory wavefronts + 43 for the table -- one per lane, every bin in a line
+                               // of its own -- of the 143 cycles an SM has per atom, profiles/r05a_cfg2_summary.txt); the texture pipe
+                               // sat idle.  tools/tex_bench.cu measured the two paths alone and against shared-memory traffic (random
+                               // 32-byte bins of a 68 MB table, 32 warps per SM: LDG 0.86 -> 0.59 bins per cycle per SM when scattered
+                               // LDS.128 compete, textures 0.66 -> 0.69).  Fused kernel: 2,032 -> 2,104 M atoms/s, issue slots 77.6 -> 81.8 %
+                               // busy (gpurun_out r05b); 2: only the first round through textures (2,099); 3: fetch predicated on the
+                               // lane having a neighbour (2,068)
 #ifndef SASA_CAP_PF
 #define SASA_CAP_PF 0          // fetch the next round's masks before the current round's ring tests
 #endif
@@ -307,9 +317,10 @@ __device__ __forceinline__ float4 make_entry_num(const float4 ai, const float4 a
 // Lane `lane` of the round starting at q0: entry + table fetch (lanes past k fetch the empty bin).
 // Atoms: accessor of the cell-sorted atoms (shared-memory array in the fused kernel, global array in the large-structure path);
 // IdxT: type of the candidate positions.
-template <class Atoms, class IdxT>
+template <bool TEX = false, class Atoms, class IdxT>
 __device__ __forceinline__ CapRound cap_fetch(const uint4 *__restrict__ tab, const Atoms &s_atom, const float4 ai, float probe,
-                                              float r2, float two_r, float inv_two_r, const IdxT *cand, int q, int k) {
+                                              float r2, float two_r, float inv_two_r, const IdxT *cand, int q, int k,
+                                              unsigned long long tex = 0ull) {
     CapRound R;
     const bool valid = q < k;
     const float4 aj = s_atom(valid ? (int)cand[q] : 0);
@@ -333,6 +344,20 @@ __device__ __forceinline__ CapRound cap_fetch(const uint4 *__restrict__ tab, con
 #else
     const int bin = valid ? (vmag >= kCapMinV2 ? cap_bin(eb, vmag) : (int)kCapBinDegenerate) : (int)kCapBinEmpty;
 #endif
+    if (TEX && (SASA_CAP_TEX != 2 || q < 32)) {   // SASA_CAP_TEX 2: the first round through the texture pipe, later rounds through LSU
+#if SASA_CAP_TEX == 3
+        R.in = make_uint4(0u, 0u, 0u, 0u);
+        R.rg = R.in;
+        if (valid) {
+            R.in = tex1Dfetch<uint4>((cudaTextureObject_t)tex, 2 * bin);
+            R.rg = tex1Dfetch<uint4>((cudaTextureObject_t)tex, 2 * bin + 1);
+        }
+#else
+        R.in = tex1Dfetch<uint4>((cudaTextureObject_t)tex, 2 * bin);
+        R.rg = tex1Dfetch<uint4>((cudaTextureObject_t)tex, 2 * bin + 1);
+#endif
+        return R;
+    }
     const uint4 *b = tab + 2 * (size_t)(unsigned)bin;
 #if SASA_CAP_LD256
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -363,9 +388,9 @@ __device__ __forceinline__ int cap_covered(unsigned a0, unsigned a1, unsigned a2
 // Lane q of round r owns neighbour 32 r + q: it builds the entry with the reference's arithmetic (make_entry), fetches
 // its bin's masks, and -- after the warp-wide OR of the inner masks -- runs the exact test on its own ring points that
 // are still uncovered.  Hits are folded into the next OR.
-template <class Atoms, class IdxT>
+template <bool TEX = false, class Atoms, class IdxT>
 __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const Atoms &s_atom, const float4 ai, float probe,
-                                        const IdxT *cand, int k, const float4 *pts, int n_points, int nbody) {
+                                        const IdxT *cand, int k, const float4 *pts, int n_points, int nbody, unsigned long long tex = 0ull) {
     const int lane = lane_id();
     const float r = __fadd_rn(ai.w, probe);
     const float r2 = __fmul_rn(r, r), two_r = __fmul_rn(2.0f, r);
@@ -373,12 +398,12 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const Ato
     unsigned a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;      // this lane's inner masks and exact hits, not yet reduced
 #if SASA_CAP_R2
     {
-        const CapRound A = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, lane, k);
+        const CapRound A = cap_fetch<TEX>(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, lane, k, tex);
         CapRound B;
         B.e = make_float4(0.f, 0.f, 0.f, 0.f);
         B.in = make_uint4(0u, 0u, 0u, 0u);
         B.rg = B.in;
-        if (k > 32) B = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, 32 + lane, k);
+        if (k > 32) B = cap_fetch<TEX>(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, 32 + lane, k, tex);
         a0 = A.in.x | B.in.x; a1 = A.in.y | B.in.y; a2 = A.in.z | B.in.z; a3 = A.in.w | B.in.w;
         const unsigned c0 = __reduce_or_sync(kFull, a0), c1 = __reduce_or_sync(kFull, a1),
                        c2 = __reduce_or_sync(kFull, a2), c3 = __reduce_or_sync(kFull, a3);
@@ -398,22 +423,22 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const Ato
     }
 #pragma unroll 1
     for (int q0 = 64; q0 < k; q0 += 32) {
-        const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, q0 + lane, k);
+        const CapRound R = cap_fetch<TEX>(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, q0 + lane, k, tex);
         cap_round(R, two_r, pts, nbody, a0, a1, a2, a3);
     }
 #elif SASA_CAP_PF
-    CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, lane, k);
+    CapRound R = cap_fetch<TEX>(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, lane, k, tex);
 #pragma unroll 1
     for (int q0 = 0; q0 < k; q0 += 32) {
         CapRound Nx = R;
-        if (q0 + 32 < k) Nx = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, q0 + 32 + lane, k);
+        if (q0 + 32 < k) Nx = cap_fetch<TEX>(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, q0 + 32 + lane, k, tex);
         cap_round(R, two_r, pts, nbody, a0, a1, a2, a3);
         R = Nx;
     }
 #else
 #pragma unroll 1
     for (int q0 = 0; q0 < k; q0 += 32) {
-        const CapRound R = cap_fetch(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, q0 + lane, k);
+        const CapRound R = cap_fetch<TEX>(tab, s_atom, ai, probe, r2, two_r, inv_two_r, cand, q0 + lane, k, tex);
         cap_round(R, two_r, pts, nbody, a0, a1, a2, a3);
     }
 #endif

@@ -59,6 +59,8 @@ struct KParams {
     // sphere points (SoA) and run parameters
     const float *px, *py, *pz;
     const uint4 *cap;             // cap table of this point set (sasa_cap.cuh), n_points <= 128 only; else null
+    unsigned long long cap_tex;   // the same table as a linear texture of uint4 (SASA_CAP_TEX: the fused kernel fetches its bins through
+                                  // the texture pipe, off the LSU data pipe that carries the shared-memory traffic); 0: none
     const uint4 *capm_in, *capm_rg;   // chunked cap table (inner / ring masks), 128 < n_points <= 1024; else null
     const float4 *pts4;           // the points as float4 (chunked cap path)
     CapDims capd;

@@ -445,10 +445,15 @@ __device__ __noinline__ float large_cold_atom(const KParams &p, const Grid &g, c
     return atom_streaming<GlobalAtoms, uint32_t, false>(p, g, atoms, cells, nullptr, pos, ent, nullptr);
 }
 
+#ifndef SASA_LARGE_TEX
+#define SASA_LARGE_TEX 16384  // structures of at least this many atoms read the cap table through the texture path in the 100-point cells
+#endif                        // kernel too (SASA_CAP_TEX; 0: never).  Measured (gpurun_out r05d): cfg4, 150 k atoms, 0.1846 -> 0.1776 ms; one
+                              // call on one small structure gets SLOWER (1,283 atoms 79 -> 92 us, 2,622 atoms 77 -> 84 us: a texture fetch
+                              // has the longer latency and these runs are latency-bound), 19 k / 32 k atoms 120 -> 119 / 160 -> 153 us
 #ifndef SASA_OPT_ULARGE
 #define SASA_OPT_ULARGE 1
 #endif
-template <int NCHP>
+template <int NCHP, bool TEX = false>
 __global__ void __launch_bounds__(256, 4) large_cells_kernel(const KParams p, int N, uint32_t a0, LargeHeader *h,
                                                              const float4 *__restrict__ sorted, const uint32_t *__restrict__ orig,
                                                              const uint32_t *__restrict__ cells, const uint32_t *__restrict__ bstart,
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(256, 4) large_cells_kernel(const KParams p, in
                     const int k = large_gather(st, total, self, ai, ai.w + reach0, nb);
                     if (k <= kLNb) {
                         if constexpr (NCHP == 1)
-                            cnt = cap_atom(p.cap, StagedAtoms{st}, ai, p.probe, nb, k, s_ptab, (int)p.n_points, nbody);
+                            cnt = cap_atom<TEX>(p.cap, StagedAtoms{st}, ai, p.probe, nb, k, s_ptab, (int)p.n_points, nbody, p.cap_tex);
                         else
                             cnt = capm_atom<NCHP, 9>(p.capm_in, p.capm_rg, p.capd, StagedAtoms{st}, ai, p.probe, nb, k, s_nbp[warp], p.pts4,
                                                      (int)p.n_points, nbody);
@@ -846,9 +851,13 @@ inline int large_enqueue(int sm_count, LargeWorkspace &w, const KParams &kp, con
         if (!cls && (kp.flags & 3u) == 0 && table) {
             const int ga = std::max(1, std::min((owned + 8 * (int)blk - 1) / (8 * (int)blk), sm_count * 4));
             // chunked tables are always laid out for eight chunks (the fused kernel shares them): one instantiation
-#define SASA_LARGE_CELLS(NCHP) large_cells_kernel<NCHP><<<ga, 256, 0, st>>>(kp, N, a0, w.hdr, w.sorted, w.orig, w.cells, w.bstart, w.val, range_rank, range_n, blk)
-            if (kp.n_points <= 128) SASA_LARGE_CELLS(1);
-            else SASA_LARGE_CELLS(8);
+#define SASA_LARGE_CELLS(NCHP, TEX) large_cells_kernel<NCHP, TEX><<<ga, 256, 0, st>>>(kp, N, a0, w.hdr, w.sorted, w.orig, w.cells, w.bstart, w.val, range_rank, range_n, blk)
+            if (kp.n_points <= 128) {
+                if (SASA_CAP_TEX && SASA_LARGE_TEX > 0 && kp.cap_tex && N >= SASA_LARGE_TEX) SASA_LARGE_CELLS(1, true);
+                else SASA_LARGE_CELLS(1, false);
+            } else {
+                SASA_LARGE_CELLS(8, false);
+            }
 #undef SASA_LARGE_CELLS
         } else {
             const int ga = std::max(1, std::min((owned + 8 * (int)blk - 1) / (8 * (int)blk), sm_count * 2));

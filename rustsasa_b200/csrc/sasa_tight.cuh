@@ -615,8 +615,8 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                         int ka, kb;
                         tight_gather2(V.atom, w_list, total, pos, pos + 1, aa, ab, aa.w + reach0, ab.w + reach0, w_cand, w_cand2, ka, kb);
                         if (ka > kNbCap || kb > kNbCap) break;   // dense neighbourhood: the one-atom path below sorts it out
-                        const int ca = cap_atom(p.cap, SmemAtoms{V.atom}, aa, p.probe, w_cand, ka, V.ptab, (int)p.n_points, nbody);
-                        const int cb = cap_atom(p.cap, SmemAtoms{V.atom}, ab, p.probe, w_cand2, kb, V.ptab, (int)p.n_points, nbody);
+                        const int ca = cap_atom<SASA_CAP_TEX != 0>(p.cap, SmemAtoms{V.atom}, aa, p.probe, w_cand, ka, V.ptab, (int)p.n_points, nbody, p.cap_tex);
+                        const int cb = cap_atom<SASA_CAP_TEX != 0>(p.cap, SmemAtoms{V.atom}, ab, p.probe, w_cand2, kb, V.ptab, (int)p.n_points, nbody, p.cap_tex);
                         pairs += (unsigned)(ka + kb);
                         if (lane < 2) V.val[(int)V.orig[pos + lane]] = (float)(lane ? cb : ca);
                         __syncwarp();
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
                                        : kNbCap + 1;
                     if (k <= kNbCap) {
 #if SASA_OPT_CAP
-                        cnt = cap_atom(p.cap, SmemAtoms{V.atom}, ai, p.probe, w_nb, k, V.ptab, (int)p.n_points, nbody);
+                        cnt = cap_atom<SASA_CAP_TEX != 0>(p.cap, SmemAtoms{V.atom}, ai, p.probe, w_nb, k, V.ptab, (int)p.n_points, nbody, p.cap_tex);
 #else
                         const float r = __fadd_rn(ai.w, p.probe);
                         const int nfront = tight_entries(V.atom, ai, p.probe, __fmul_rn(r, r), __fmul_rn(2.0f, r), p.near2,
