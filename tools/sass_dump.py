@@ -15,8 +15,9 @@ LIB = os.path.join(ROOT, "rustsasa_b200", "libsasa_b200.so")
 WANT = {
     "tight_1024": "_ZN4sasa17sasa_tight_kernelILi1024ELi1ELb0ELj16384ELi3EEEvNS_7KParamsE",
     "small_1024": "_ZN4sasa17sasa_small_kernelILi1024ELi1ELb0ELj16384EEEvNS_7KParamsE",
-    "large_cells_1": "_ZN4sasa18large_cells_kernelILi1EEE",
-    "large_cells_8": "_ZN4sasa18large_cells_kernelILi8EEE",
+    "large_cells_1": "_ZN4sasa18large_cells_kernelILi1ELb0EEE",
+    "large_cells_1_tex": "_ZN4sasa18large_cells_kernelILi1ELb1EEE",
+    "large_cells_8": "_ZN4sasa18large_cells_kernelILi8ELb0EEE",
     "large_atoms": "_ZN4sasa18large_atoms_kernelE",
     "large_scan": "_ZN4sasa17large_scan_kernelE",
 }
@@ -46,7 +47,7 @@ def main():
             base[k.split(".")[0]] += v
         summary.append(f"## {short}  ({mangled[:70]}...)  {n} instructions\n")
         summary.append("  by opcode: " + ", ".join(f"{k} {v}" for k, v in base.most_common(28)) + "\n")
-        keys = [k for k in ops if re.match(r"(LDS|STS|LDG|STG|LDC|REDUX|CREDUX|VOTE|SHFL|ATOMS|ATOMG|RED|MUFU|BAR|LDGSTS|UTMA|MATCH|POPC|FFMA|FSETP)", k)]
+        keys = [k for k in ops if re.match(r"(LDS|STS|LDG|STG|LDC|TLD|TEX|REDUX|CREDUX|VOTE|SHFL|ATOMS|ATOMG|RED|MUFU|BAR|LDGSTS|UTMA|MATCH|POPC|FFMA|FSETP)", k)]
         summary.append("  memory / collective / fp forms: " + ", ".join(f"{k} {ops[k]}" for k in sorted(keys, key=lambda k: -ops[k])[:40]) + "\n\n")
     with open(os.path.join(ROOT, "profiles", f"{tag}_sass_summary.txt"), "w") as fh:
         fh.writelines(summary)
