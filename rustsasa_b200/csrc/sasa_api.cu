@@ -982,6 +982,10 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
     J_TRY(cudaEventRecord(job->ev0, s0));
     for (int i = 1; i < kStreams; ++i) J_TRY(cudaStreamWaitEvent(ctx->streams[i], job->ev0, 0));
     size_t ci = 0;
+    // SASA_B200_TRACE_CHUNKS=1 (debugging aid): events around every chunk's kernels; the run is synchronised and the start / end
+    // of each chunk relative to the job's first event printed to stderr
+    static const bool trace_chunks = getenv("SASA_B200_TRACE_CHUNKS") != nullptr;
+    std::vector<cudaEvent_t> trace_ev;
     // the large-structure workspace is shared by all chunks: keep such batches on a single stream
     const int nstreams = b->max_large_v[variant] ? 1 : kStreams;
     for (const Chunk &ch : b->plan[variant]) {
@@ -1007,7 +1011,19 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
             }
             if (id_class) J_TRY(cudaMemcpyAsync(base_p + o_cls + ch.a0 * 4, id_class + ch.a0, na * 4, cudaMemcpyHostToDevice, st));
         }
+        if (trace_chunks) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            trace_ev.push_back(e);
+        }
         if ((rc = enqueue_chunk(b, variant, ch, kbase, st, &job->launches)) != 0) return job_abort(ctx, job, rc);
+        if (trace_chunks) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, st);
+            trace_ev.push_back(e);
+        }
         if (na && out->counts)
             J_TRY(cudaMemcpyAsync(out->counts + ch.a0, base_p + o_cnt + ch.a0 * 4, na * 4, cudaMemcpyDeviceToHost, st));
         if (na && out->atom_sasa)
@@ -1026,6 +1042,20 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
     ctx->tail_valid = true;
     J_TRY(cudaMemcpyAsync(job->h_status, d_status, 32, cudaMemcpyDeviceToHost, s0));
     J_TRY(cudaEventRecord(job->ev1, s0));
+    if (trace_chunks) {
+        cudaEventSynchronize(job->ev1);
+        float t_end = 0.f;
+        cudaEventElapsedTime(&t_end, job->ev0, job->ev1);
+        fprintf(stderr, "[sasa_b200] chunk trace (ms after the job's first event; whole job %.3f):", t_end);
+        for (size_t i = 0; i + 1 < trace_ev.size(); i += 2) {
+            float a = 0.f, z = 0.f;
+            cudaEventElapsedTime(&a, job->ev0, trace_ev[i]);
+            cudaEventElapsedTime(&z, job->ev0, trace_ev[i + 1]);
+            fprintf(stderr, " [%zu: %.3f-%.3f, %zu atoms]", i / 2, a, z, (size_t)(b->plan[variant][i / 2].a1 - b->plan[variant][i / 2].a0));
+        }
+        fprintf(stderr, "\n");
+        for (cudaEvent_t e : trace_ev) cudaEventDestroy(e);
+    }
     J_TRY(cudaFreeAsync(job->d_arena, s0));
     job->d_arena = nullptr;
 #undef J_TRY
