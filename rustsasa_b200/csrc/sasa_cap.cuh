@@ -463,6 +463,8 @@ __device__ __forceinline__ int cap_atom(const uint4 *__restrict__ tab, const Ato
 }
 
 // ---- chunked cap tables: 128 < n_points <= 1024 --------------------------------------------------------------------------
+// Tried and dropped (gpurun_out r05i): prefetch.global.L1 of each neighbour's inner-mask line as soon as its bin is known
+// (cfg5 1.618 -> 1.627 ms).
 #ifndef SASA_CAPM_UNROLL
 #define SASA_CAPM_UNROLL 2     // pass-1 loop unroll.  Measured on cfg5 (gpurun_out r02l): 2 -> 1.60 ms, 4 -> 1.93 ms (spills), 8 -> 1.62 ms;
 #endif                         // a 96^2 / 128^2 direction grid gives 1.55 / 1.54 ms for 2.3x / 4x the table (kept at 64^2)
