@@ -107,6 +107,7 @@ namespace sasa {
 #ifndef SASA_OPT_NOGUARD
 #define SASA_OPT_NOGUARD 1    // 1: the neighbour lists of the cap path live in the idle entry strip with room for every listed
 #endif                        // candidate, so the gather needs no capacity test on its stores
+#define SASA_NOGUARD_ON (SASA_OPT_NOGUARD && SASA_OPT_CAP)   // (the two-phase build keeps its 128-entry lists and their capacity test)
 #ifndef SASA_OPT_NEXT
 #define SASA_OPT_NEXT 1       // warp 0 claims the CTA's next structure and prefetches its atoms into L2 while the other
                               // warps already work on the current one (hides the claim / first-touch latency of the setup)
@@ -233,7 +234,7 @@ __device__ __forceinline__ int tight_gather(const float4 *s_atom, const uint32_t
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const int at = k + __popc(m[g] & lt);
-            if (SASA_OPT_NOGUARD ? acc[g] : (acc[g] & (at < kQueueCap))) cand[at] = (uint16_t)j[g];
+            if (SASA_NOGUARD_ON ? acc[g] : (acc[g] & (at < kQueueCap))) cand[at] = (uint16_t)j[g];
             k += __popc(m[g]);
         }
     }
@@ -248,7 +249,7 @@ __device__ __forceinline__ int tight_gather(const float4 *s_atom, const uint32_t
         if (HAS_CLS) acc = acc && (s_cls[j] != cls_i);
         const unsigned m = __ballot_sync(kFull, acc);
         const int at = k + __popc(m & lt);
-        if (SASA_OPT_NOGUARD ? acc : (acc & (at < kQueueCap))) cand[at] = (uint16_t)j;
+        if (SASA_NOGUARD_ON ? acc : (acc & (at < kQueueCap))) cand[at] = (uint16_t)j;
         k += __popc(m);
     }
 #else
@@ -294,8 +295,8 @@ __device__ __forceinline__ void tight_gather2(const float4 *s_atom, const uint16
         const bool acc_a = (d2a <= ca * ca) & (j != pos_a), acc_b = (d2b <= cb * cb) & (j != pos_b);   // sentinel pads fail both
         const unsigned ma = __ballot_sync(kFull, acc_a), mb = __ballot_sync(kFull, acc_b);
         const int at_a = k0 + __popc(ma & lt), at_b = k1 + __popc(mb & lt);
-        if (SASA_OPT_NOGUARD ? acc_a : (acc_a & (at_a < kQueueCap))) cand_a[at_a] = (uint16_t)j;
-        if (SASA_OPT_NOGUARD ? acc_b : (acc_b & (at_b < kQueueCap))) cand_b[at_b] = (uint16_t)j;
+        if (SASA_NOGUARD_ON ? acc_a : (acc_a & (at_a < kQueueCap))) cand_a[at_a] = (uint16_t)j;
+        if (SASA_NOGUARD_ON ? acc_b : (acc_b & (at_b < kQueueCap))) cand_b[at_b] = (uint16_t)j;
         k0 += __popc(ma);
         k1 += __popc(mb);
     }
