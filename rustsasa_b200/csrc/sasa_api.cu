@@ -54,7 +54,10 @@ struct SmallCfg {
     int proto;
 };
 
-constexpr int kStreams = 3;
+#ifndef SASA_STREAMS
+#define SASA_STREAMS 3   // streams of the pipelined host entry points.  cfg2 end to end, device-side span (tools/exp_e2e.py, one B200): 2 streams
+#endif                   // 5.92 ms, 3: 5.26 ms, 4: 5.29 ms, 6: 5.37 ms (5.00 ms as one device-resident launch)
+constexpr int kStreams = SASA_STREAMS;
 constexpr size_t kChunkAtoms = 1000000;
 constexpr uint32_t kSingleLargeMin = 1024;   // atoms from which a lone structure takes the large-structure path
 constexpr size_t kMaxSlots = 16;
