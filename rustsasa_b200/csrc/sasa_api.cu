@@ -59,6 +59,8 @@ struct SmallCfg {
 #endif                   // 5.92 ms, 3: 5.26 ms, 4: 5.29 ms, 6: 5.37 ms (5.00 ms as one device-resident launch)
 constexpr int kStreams = SASA_STREAMS;
 constexpr size_t kChunkAtoms = 1000000;
+constexpr size_t kMaxGatedChunks = 1024;              // chunks of one gated single-launch run (more: the per-chunk launches)
+constexpr size_t kGatedMaxOutBytes = 32u << 20;        // outputs above this go through device memory and D2H copies
 constexpr uint32_t kSingleLargeMin = 1024;   // atoms from which a lone structure takes the large-structure path
 constexpr size_t kMaxSlots = 16;
 
@@ -81,6 +83,7 @@ struct sasa_b200_job {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // timing: first enqueue .. everything done
     void *d_arena = nullptr;                    // stream-ordered allocation holding inputs, outputs and the status words
     unsigned long long *h_status = nullptr;     // pinned: [0] error flag, [1..3] statistics
+    uint32_t *h_ready = nullptr;                // pinned: cumulative structure counts of the chunks (gated single-launch pipeline)
     std::chrono::steady_clock::time_point t_begin;
     uint32_t launches = 0;
     bool active = false;
@@ -295,6 +298,10 @@ struct sasa_b200_batch {
     // mode: 0 = chunked for the pipelined host entry points, 1 = one chunk for device-resident runs
     std::vector<Chunk> plan[4];
     std::vector<uint32_t> h_order[4];
+    // gated single-launch pipeline (host plans 0 / 1 only): the whole batch as ONE queue in an order that follows the arrival of
+    // the chunks, and per queue position the number of chunks that must have arrived (empty: the plan does not qualify)
+    std::vector<uint32_t> h_gorder[2], h_gneed[2];
+    uint32_t *d_gorder[2] = {nullptr, nullptr}, *d_gneed[2] = {nullptr, nullptr};
     uint32_t n_counters[4] = {0, 0, 0, 0};
     uint32_t max_large = 0;             // largest structure that takes the large-structure path in ANY plan (workspace size)
     uint32_t max_large_v[4] = {0, 0, 0, 0};   // ... per plan: a structure may fit the fused kernels without id classes only
@@ -308,6 +315,53 @@ struct sasa_b200_batch {
 };
 
 namespace {
+
+// Queue of the gated single-launch pipeline.  The per-chunk launches work every chunk largest-first, so big structures turn up
+// all the way to the end of the batch; one launch over a chunk-major queue inherits that (measured: 5.21 ms against 5.00 ms for
+// the batch-wide largest-first order of a device-resident run).  But a structure may be queued anywhere after its chunk has
+// arrived, and the copies run ahead of the kernels -- so the queue is built by simulation: work proceeds at one atom per unit of
+// time, chunk c has arrived once kGatedRate x time has passed its last atom, and every position takes the LARGEST structure that
+// has arrived.  After the copies are done (half way through the work at the real copy rate) what is left is in exact
+// largest-first order.  The rate assumed here is deliberately below the real ratio of copy to compute speed (about 2 for the 13-byte
+// wire format): where it is still too optimistic a CTA waits at the gate for a moment, never wrongly.
+constexpr double kGatedRate = 1.25;
+void build_gated_order(sasa_b200_batch *b, int variant) {
+    std::vector<uint32_t> &order = b->h_gorder[variant], &need = b->h_gneed[variant];
+    order.clear();
+    need.clear();
+    const std::vector<Chunk> &plan = b->plan[variant];
+    if (b->max_large_v[variant] != 0 || plan.size() < 2 || plan.size() > kMaxGatedChunks) return;
+    const int cfg0 = plan[0].launches.empty() ? -1 : plan[0].launches[0].cfg;
+    for (const Chunk &ch : plan)
+        if (ch.launches.size() != 1 || ch.launches[0].cfg < 0 || ch.launches[0].cfg != cfg0) return;
+    auto atoms_of = [&](uint32_t sidx) { return b->h_off[sidx + 1] - b->h_off[sidx]; };
+    std::vector<std::pair<uint32_t, uint32_t>> heap;   // (atoms, structure), max-heap; ties: lower structure index first
+    auto less = [](const std::pair<uint32_t, uint32_t> &x, const std::pair<uint32_t, uint32_t> &y) {
+        return x.first != y.first ? x.first < y.first : x.second > y.second;
+    };
+    std::vector<uint32_t> chunk_of(b->S, 0);
+    size_t next_chunk = 0;
+    double t = 0.0;
+    auto arrive = [&]() {
+        const Chunk &ch = plan[next_chunk];
+        for (uint32_t i = ch.s0; i < ch.s1; ++i) {
+            chunk_of[i] = (uint32_t)next_chunk;
+            heap.emplace_back(atoms_of(i), i);
+            std::push_heap(heap.begin(), heap.end(), less);
+        }
+        ++next_chunk;
+    };
+    arrive();
+    while (order.size() < b->S) {
+        while (next_chunk < plan.size() && (heap.empty() || (double)(plan[next_chunk].a1 - plan[0].a1) <= kGatedRate * t)) arrive();
+        std::pop_heap(heap.begin(), heap.end(), less);
+        const std::pair<uint32_t, uint32_t> top = heap.back();
+        heap.pop_back();
+        order.push_back(top.second);
+        need.push_back(chunk_of[top.second] + 1);
+        t += (double)top.first;
+    }
+}
 
 int arena_reserve(sasa_b200_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->arena_bytes) return SASA_B200_OK;
@@ -341,7 +395,8 @@ void build_plan(sasa_b200_batch *b, int variant) {
         ch.s0 = s;
         ch.a0 = b->h_off[s];
         // the first chunks are smaller so that the first kernel starts after a short copy (ramp 1/8, 1/4, 1/2, 1, 1, ...)
-        const size_t ramp = plan.size() < 3 && chunk_atoms != ~(size_t)0 ? chunk_atoms >> (3 - plan.size()) : chunk_atoms;
+        static const size_t ramp_levels = [] { const char *e = getenv("SASA_B200_RAMP"); return e ? (size_t)atoi(e) : (size_t)3; }();
+        const size_t ramp = plan.size() < ramp_levels && chunk_atoms != ~(size_t)0 ? chunk_atoms >> (ramp_levels - plan.size()) : chunk_atoms;
         while (s < b->S && (b->h_off[s] - ch.a0 < ramp || s == ch.s0)) ++s;
         // equal-sized structures (MD frames) finish in lock step: cut the chunk at a whole number of waves of the
         // widest configuration so that no launch ends with a mostly idle last round
@@ -491,7 +546,7 @@ int check_params(sasa_b200_ctx *ctx, const sasa_b200_params *p) {
 // joined back into `st` (so the caller still sees one stream-ordered unit of work).  Large-structure pipelines stay
 // on `st`.
 int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParams &base, cudaStream_t st,
-                  uint32_t *launches) {
+                  uint32_t *launches, const uint32_t *order_override = nullptr) {
     sasa_b200_ctx *ctx = b->ctx;
     int n_small = 0;
     for (const Launch &L : ch.launches) n_small += L.cfg >= 0;
@@ -503,7 +558,7 @@ int enqueue_chunk(sasa_b200_batch *b, int variant, const Chunk &ch, const KParam
     int small_idx = 0, forked = 0;
     for (const Launch &L : ch.launches) {
         KParams kp = base;
-        kp.order = b->d_order[variant] + L.order_off;
+        kp.order = order_override ? order_override : b->d_order[variant] + L.order_off;
         kp.n_work = L.n_work;
         kp.work_counter = b->d_counters + L.counter;
         if (L.cfg < 0) {
@@ -671,6 +726,7 @@ void sasa_b200_destroy(sasa_b200_ctx *ctx) {
         cudaEventDestroy(j->ev0);
         cudaEventDestroy(j->ev1);
         cudaFreeHost(j->h_status);
+        cudaFreeHost(j->h_ready);
         delete j;
     }
     for (auto &sp : ctx->slots) {
@@ -752,6 +808,7 @@ static int batch_create_impl(sasa_b200_ctx *ctx, const uint64_t *struct_off, siz
         }
     }
     for (int v = 0; v < 4; ++v) build_plan(b, v);
+    for (int v = 0; v < 2; ++v) build_gated_order(b, v);
 #define B_TRY(expr)                                                                                            \
     do {                                                                                                       \
         cudaError_t e__ = (expr);                                                                              \
@@ -767,6 +824,13 @@ static int batch_create_impl(sasa_b200_ctx *ctx, const uint64_t *struct_off, siz
         B_TRY(cudaMallocAsync(&b->d_order[v], std::max<size_t>(1, b->h_order[v].size()) * sizeof(uint32_t), ps));
         if (!b->h_order[v].empty())
             B_TRY(cudaMemcpyAsync(b->d_order[v], b->h_order[v].data(), b->h_order[v].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ps));
+    }
+    for (int v = 0; v < 2; ++v) {
+        if (b->h_gorder[v].empty()) continue;
+        B_TRY(cudaMallocAsync(&b->d_gorder[v], b->h_gorder[v].size() * sizeof(uint32_t), ps));
+        B_TRY(cudaMallocAsync(&b->d_gneed[v], b->h_gneed[v].size() * sizeof(uint32_t), ps));
+        B_TRY(cudaMemcpyAsync(b->d_gorder[v], b->h_gorder[v].data(), b->h_gorder[v].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ps));
+        B_TRY(cudaMemcpyAsync(b->d_gneed[v], b->h_gneed[v].data(), b->h_gneed[v].size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ps));
     }
     B_TRY(cudaMallocAsync(&b->d_counters, std::max<uint32_t>(1, *std::max_element(b->n_counters, b->n_counters + 4)) * sizeof(uint32_t), ps));
     if (b->n_seg) {
@@ -805,6 +869,10 @@ void sasa_b200_batch_destroy(sasa_b200_batch *b) {
     if (b->d_seg_off) cudaFreeAsync(b->d_seg_off, ps);
     for (int v = 0; v < 4; ++v)
         if (b->d_order[v]) cudaFreeAsync(b->d_order[v], ps);
+    for (int v = 0; v < 2; ++v) {
+        if (b->d_gorder[v]) cudaFreeAsync(b->d_gorder[v], ps);
+        if (b->d_gneed[v]) cudaFreeAsync(b->d_gneed[v], ps);
+    }
     if (b->d_counters) cudaFreeAsync(b->d_counters, ps);
     if (b->d_seg_be) cudaFreeAsync(b->d_seg_be, ps);
     if (b->d_polar) cudaFreeAsync(b->d_polar, ps);
@@ -863,9 +931,12 @@ static sasa_b200_job *job_acquire(sasa_b200_ctx *ctx) {
     } else {
         j = new sasa_b200_job();
         if (cudaEventCreate(&j->ev0) != cudaSuccess || cudaEventCreate(&j->ev1) != cudaSuccess ||
-            cudaHostAlloc((void **)&j->h_status, 4 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) {
+            cudaHostAlloc((void **)&j->h_status, 4 * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc((void **)&j->h_ready, kMaxGatedChunks * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) {
             if (j->ev0) cudaEventDestroy(j->ev0);
             if (j->ev1) cudaEventDestroy(j->ev1);
+            if (j->h_status) cudaFreeHost(j->h_status);
+            if (j->h_ready) cudaFreeHost(j->h_ready);
             delete j;
             return nullptr;
         }
@@ -962,6 +1033,39 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
     ra.d_out.atom_sasa = out->atom_sasa ? reinterpret_cast<float *>(base_p + o_atom) : nullptr;
     ra.d_out.seg_sasa = (out->seg_sasa && G) ? reinterpret_cast<float *>(base_p + o_seg) : nullptr;
     ra.d_out.protein = out->protein ? reinterpret_cast<float *>(base_p + o_prot) : nullptr;
+    // ---- gated single-launch pipeline ----------------------------------------------------------------------------------
+    // Thirteen launches of 148 persistent CTAs cost the pipelined run 0.25 ms over the same work as ONE launch (CTA start-ups
+    // with a cold first structure, per-chunk instead of batch-wide queue).  When every chunk of the plan is one
+    // launch of the same fused configuration, the whole batch is therefore ONE launch over the chunk-major queue: the copy
+    // stream raises a counter in device memory after every chunk's copy, a CTA that claims a queue position beyond it waits
+    // (wait_ready, sasa_small.cuh), and the kernel writes its results straight into the caller's page-locked buffers --
+    // there is no D2H stage to order behind individual chunks.  Needs outputs the device can address (pinned / registered
+    // host memory) of moderate size; anything else takes the per-chunk launches below.
+    static const bool gated_env = [] { const char *e = getenv("SASA_B200_GATED"); return !e || atoi(e) != 0; }();
+    bool gated = gated_env && variant < 2 && !b->h_gorder[variant].empty();
+    if (gated) {
+        const size_t out_bytes = (out->counts ? N * 4 : 0) + (out->atom_sasa ? N * 4 : 0) + ((out->seg_sasa && G) ? G * 4 : 0) +
+                                 (out->protein ? S * 12 : 0);
+        if (out_bytes > kGatedMaxOutBytes) gated = false;
+        auto mapped = [&](const void *host, void **dev) {
+            if (!host) { *dev = nullptr; return true; }
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return false; }
+            if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+            *dev = at.devicePointer;
+            return true;
+        };
+        void *dc = nullptr, *da = nullptr, *ds = nullptr, *dp = nullptr;
+        if (gated && mapped(out->counts, &dc) && mapped(out->atom_sasa, &da) && mapped((out->seg_sasa && G) ? out->seg_sasa : nullptr, &ds) &&
+            mapped(out->protein, &dp)) {
+            ra.d_out.counts = static_cast<uint32_t *>(dc);
+            ra.d_out.atom_sasa = static_cast<float *>(da);
+            ra.d_out.seg_sasa = static_cast<float *>(ds);
+            ra.d_out.protein = static_cast<float *>(dp);
+        } else {
+            gated = false;
+        }
+    }
     ra.prm = *params;
     ra.pts = pts;
     KParams kbase;
@@ -979,7 +1083,7 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
         kbase.radii = reinterpret_cast<const float *>(base_p + o_rad);
         if (indexed) kbase.ridx = reinterpret_cast<const uint8_t *>(base_p + o_ridx);
     }
-    J_TRY(cudaMemsetAsync(d_status, 0, 32, s0));
+    J_TRY(cudaMemsetAsync(d_status, 0, 128, s0));   // status words + the ready counter of the gated pipeline (at +64 bytes)
     if (b->n_counters[variant]) J_TRY(cudaMemsetAsync(b->d_counters, 0, b->n_counters[variant] * sizeof(uint32_t), s0));
     if (frames && fN) J_TRY(cudaMemcpyAsync(base_p + o_rad, radii, fN * 4, cudaMemcpyHostToDevice, s0));
     J_TRY(cudaEventRecord(job->ev0, s0));
@@ -991,6 +1095,37 @@ static int submit_host_impl(sasa_b200_batch *b, const float *xyzr, const float *
     std::vector<cudaEvent_t> trace_ev;
     // the large-structure workspace is shared by all chunks: keep such batches on a single stream
     const int nstreams = b->max_large_v[variant] ? 1 : kStreams;
+    if (gated) {
+        // the one kernel first (it starts at once and waits for chunk 0 at the gate), then the copies on the first stream
+        uint32_t *d_ready = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(d_status) + 64);
+        KParams kg = kbase;
+        kg.ready = d_ready;
+        kg.need = b->d_gneed[variant];
+        Chunk all;
+        all.s0 = 0; all.s1 = (uint32_t)S; all.a0 = 0; all.a1 = N; all.g0 = 0; all.g1 = G;
+        Launch L = b->plan[variant][0].launches[0];
+        L.n_work = 0;
+        for (const Chunk &ch : b->plan[variant]) L.n_work += ch.launches[0].n_work;
+        all.launches.push_back(L);
+        cudaStream_t sk = ctx->streams[1];
+        if ((rc = enqueue_chunk(b, variant, all, kg, sk, &job->launches, b->d_gorder[variant])) != 0) return job_abort(ctx, job, rc);
+        size_t c = 0;
+        for (const Chunk &ch : b->plan[variant]) {
+            const size_t na = ch.a1 - ch.a0;
+            if (na) {
+                if (frames) {
+                    J_TRY(cudaMemcpyAsync(base_p + o_xyz3 + ch.a0 * 12, xyz3 + ch.a0 * 3, na * 12, cudaMemcpyHostToDevice, s0));
+                    if (indexed) J_TRY(cudaMemcpyAsync(base_p + o_ridx + ch.a0, ridx + ch.a0, na, cudaMemcpyHostToDevice, s0));
+                } else {
+                    J_TRY(cudaMemcpyAsync(base_p + o_xyzr + ch.a0 * 16, xyzr + ch.a0 * 4, na * 16, cudaMemcpyHostToDevice, s0));
+                }
+                if (id_class) J_TRY(cudaMemcpyAsync(base_p + o_cls + ch.a0 * 4, id_class + ch.a0, na * 4, cudaMemcpyHostToDevice, s0));
+            }
+            job->h_ready[c] = (uint32_t)(c + 1);
+            J_TRY(cudaMemcpyAsync(d_ready, &job->h_ready[c], sizeof(uint32_t), cudaMemcpyHostToDevice, s0));
+            ++c;
+        }
+    } else
     for (const Chunk &ch : b->plan[variant]) {
         cudaStream_t st = ctx->streams[ci++ % nstreams];
         const size_t na = ch.a1 - ch.a0;

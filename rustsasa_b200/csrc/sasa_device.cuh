@@ -43,6 +43,9 @@ struct KParams {
     const uint32_t *order;        // structures handled by this launch
     uint32_t n_work;
     uint32_t *work_counter;
+    const uint32_t *ready;        // gate of the single-launch host pipeline (sasa_api.cu): the number of input chunks that have arrived in
+    const uint32_t *need;         // device memory -- the copy stream raises it after every chunk -- and, per queue position, how many
+                                  // chunks that position's structure needs.  null: everything is there
     const uint2 *seg_be;          // nullable
     const uint32_t *struct_seg_off;
     const uint8_t *seg_polar;     // nullable

@@ -386,10 +386,34 @@ __device__ __forceinline__ void structure_outputs(const KParams &p, const SmemVi
     }
 }
 
+// Gate of the single-launch host pipeline: queue position w may be worked on once the copy stream has raised *p.ready to
+// p.need[w], the number of input chunks its structure needs (the counter is copied after the data, in stream order).  One thread
+// polls with an acquire load at system scope; the caller's barrier publishes the result to the CTA.  The wait is bounded: a
+// copy that never arrives raises the error flag instead of hanging the device.
+__device__ __forceinline__ void wait_ready(const KParams &p, uint32_t w) {
+    if (!p.ready) return;
+    const uint32_t need = __ldg(p.need + w);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready) : "memory");
+        if (v >= need) return;
+        __nanosleep(200);
+        if (clock64() - t0 > (1ll << 33)) {   // about four seconds
+            atomicExch(p.err_flag, 2);
+            return;
+        }
+    }
+}
+
 // Claim the next structure of this launch for the CTA (largest-first order prepared by the host).
 __device__ __forceinline__ bool claim_structure(const KParams &p, int *misc, uint32_t &sid, uint32_t &a0, int &N) {
     __syncthreads();
-    if (threadIdx.x == 0) misc[0] = (int)atomicAdd(p.work_counter, 1u);
+    if (threadIdx.x == 0) {
+        const uint32_t w = atomicAdd(p.work_counter, 1u);
+        misc[0] = (int)w;
+        if (w < p.n_work) wait_ready(p, w);
+    }
     __syncthreads();
     const uint32_t w = (uint32_t)misc[0];
     if (w >= p.n_work) return false;
@@ -408,6 +432,7 @@ __device__ __forceinline__ void claim_next_and_prefetch(const KParams &p, int *m
     uint32_t na0 = 0, nN = 0;
     if (lane == 0) {
         const uint32_t w = atomicAdd(p.work_counter, 1u);
+        misc[0] = (int)w;   // claim_prefetched waits for this queue position's data (wait_ready)
         uint32_t nsid = 0;
         if (w < p.n_work) {
             nsid = p.order[w];
@@ -426,8 +451,12 @@ __device__ __forceinline__ void claim_next_and_prefetch(const KParams &p, int *m
     for (size_t o = (size_t)lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
 }
 
-__device__ __forceinline__ bool claim_prefetched(int *misc, uint32_t &sid, uint32_t &a0, int &N) {
+__device__ __forceinline__ bool claim_prefetched(const KParams &p, int *misc, uint32_t &sid, uint32_t &a0, int &N) {
     __syncthreads();
+    if (p.ready) {   // (uniform) the prefetch may have run ahead of the copy; the loads of the setup must not
+        if (threadIdx.x == 0 && misc[2]) wait_ready(p, (uint32_t)misc[0]);
+        __syncthreads();
+    }
     const int have = misc[2];
     sid = (uint32_t)misc[3];
     a0 = (uint32_t)misc[4];

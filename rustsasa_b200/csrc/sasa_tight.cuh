@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(NT, MINB) sasa_tight_kernel(const KParams p) {
     int N;
 #if SASA_OPT_NEXT
     bool first = true;
-    while (first ? claim_structure(p, V.misc, sid, a0, N) : claim_prefetched(V.misc, sid, a0, N)) {
+    while (first ? claim_structure(p, V.misc, sid, a0, N) : claim_prefetched(p, V.misc, sid, a0, N)) {
         first = false;
 #else
     while (claim_structure(p, V.misc, sid, a0, N)) {

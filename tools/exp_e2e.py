@@ -33,6 +33,14 @@ for _ in range(10):
     ws.append((time.perf_counter() - t0) * 1e3)
     ks.append(r.stats["kernel_ms"])
     ts.append(r.stats["total_ms"])
+h_x4 = eng.pinned_empty((N, 4), np.float32)
+h_x4[...] = data.xyzr
+for _ in range(3):
+    b.run_host(h_x4, want=("seg",), result=res)
+k4 = []
+for _ in range(10):
+    k4.append(b.run_host(h_x4, want=("seg",), result=res).stats["kernel_ms"])
+print(f"float4 wire format: device span {np.median(k4):.3f} ms")
 d_xyzr = torch.from_numpy(data.xyzr).cuda()
 d_seg = torch.zeros(G, dtype=torch.float32, device="cuda")
 for _ in range(3):

@@ -37,6 +37,12 @@ check("indexed wire format", np.array_equal(r2.counts, r.counts) and np.array_eq
 j = b.submit_host(d.xyzr)
 r3 = j.wait()
 check("submit / wait", np.array_equal(np.asarray(r3.counts), r.counts))
+# page-locked outputs: with more than one chunk in the plan (tools/gpu_sanitize.sh sets SASA_B200_CHUNK_ATOMS=4000) this is the
+# gated single-launch pipeline -- one kernel, results stored straight into host memory
+rp = b.run_host(d.xyzr, result=b._host_outputs(("counts", "atom", "seg", "protein"), "pinned"))
+check(f"page-locked outputs ({rp.stats['gpu_launches']} launch(es)) == pageable outputs ({r.stats['gpu_launches']})",
+      np.array_equal(np.asarray(rp.counts), r.counts) and np.array_equal(np.asarray(rp.seg_sasa), r.seg_sasa)
+      and np.array_equal(np.asarray(rp.protein), r.protein) and np.array_equal(np.asarray(rp.atom_sasa), r.atom_sasa))
 r4 = b.run_host(d.xyzr, n_points=300, want=("counts",))
 o4 = orc.run_batch(d.xyzr, d.struct_off, 1.4, 300)
 check("generic fused kernel with the chunked table (300 points)", np.array_equal(r4.counts, o4["counts"]))
