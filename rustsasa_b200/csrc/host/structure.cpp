@@ -298,6 +298,32 @@ double parse_double(std::string_view s) {
     s = trim(s);
     std::string_view t = s;
     if (!t.empty() && t.front() == '+') t.remove_prefix(1);
+    {   // fast path for plain decimals (what coordinate, occupancy and B-factor columns hold): an integer mantissa below 2^53
+        // over an exact power of ten is ONE correctly rounded division -- the same double a correctly rounded decimal parser
+        // (from_chars below, Rust's str::parse::<f64> in the reference) returns
+        static const double kPow10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+        const char *q = t.data(), *const end = q + t.size();
+        const bool neg = q < end && *q == '-';
+        if (neg) ++q;
+        unsigned long long m = 0;
+        int digits = 0, frac = -1;
+        for (; q < end; ++q) {
+            const unsigned d = (unsigned)(*q - '0');
+            if (d <= 9) {
+                m = m * 10 + d;
+                ++digits;
+                if (frac >= 0) ++frac;
+            } else if (*q == '.' && frac < 0) {
+                frac = 0;
+            } else {
+                break;
+            }
+        }
+        if (q == end && digits > 0 && digits <= 15) {
+            const double v = (double)m / kPow10[frac < 0 ? 0 : frac];
+            return neg ? -v : v;
+        }
+    }
     double v = 0.0;
     const auto r = std::from_chars(t.data(), t.data() + t.size(), v, std::chars_format::general);
     if (r.ec == std::errc() && r.ptr == t.data() + t.size()) return v;

@@ -297,6 +297,25 @@ def test_number_fields_parse_like_the_mirror(host, tmp_path):
     assert np.allclose(got["xyzr"][0, :3], [20.154, -16.967, 25.0]) and np.allclose(got["xyzr"][4, :3], [10.0, 0.5, 0.0])
 
 
+def test_decimal_fast_path_matches_correctly_rounded_parse(host, tmp_path):
+    """The reader's fast path for plain decimals (integer mantissa / exact power of ten, one IEEE division) must give the double a
+    correctly rounded decimal parser gives -- Python's float() here, Rust's str::parse::<f64> in the reference -- and hence the same
+    f32 coordinate: 3,000 random %8.3f fields of every magnitude and sign the column holds, compared bit for bit."""
+    rng = np.random.default_rng(7)
+    vals = np.concatenate([rng.uniform(-999.999, 9999.999, 2000), rng.uniform(-1.0, 1.0, 700), rng.uniform(-99.0, 99.0, 300)])
+    lines = []
+    for i in range(0, vals.size, 3):
+        x, y, z = vals[i:i + 3]
+        lines.append("ATOM  %5d  CA  ALA A%4d    %8.3f%8.3f%8.3f  1.00  0.00           C" % (i // 3 + 1, i // 3 + 1, x, y, z))
+    f = tmp_path / "r.pdb"
+    f.write_text("\n".join(lines) + "\nEND\n")
+    got = host.pack(str(f), "atom")
+    want = np.array([[float("%8.3f" % v) for v in vals[i:i + 3]] for i in range(0, vals.size, 3)], np.float64).astype(np.float32)
+    assert got["xyzr"].shape[0] == want.shape[0]
+    assert np.array_equal(got["xyzr"][:, :3].view(np.uint32), want.view(np.uint32))
+    assert check_same(host, str(f), "residue") is not None
+
+
 def test_residue_and_chain_json_shape(host):
     """serde's externally tagged enum with the struct fields in declaration order (src/structures/atomic.rs:26-70,
     SURVEY.md 8f row f-3)."""
