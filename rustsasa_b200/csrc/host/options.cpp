@@ -162,6 +162,35 @@ void set_device(int device) {
 Packed build_atoms_and_mapping(const pdb::PDB &pdb, LevelKind level, const OptionValues &opt) {
     Packed out;
     const RadiiConfig *custom = opt.radii_config.get();
+    {
+        const size_t n = pdb.atom_count();
+        out.xyzr.reserve(4 * n);
+        out.ids.reserve(n);
+    }
+    // get_radius (src/utils.rs:40-56: custom[residue][atom], else ProtOr[residue][atom]) with the residue's two inner tables
+    // looked up once per residue instead of once per atom
+    using Inner = std::unordered_map<std::string, float>;
+    const Inner *custom_res = nullptr, *protor_res = nullptr;
+    auto set_residue = [&](const std::string &resname) {   // called once per residue, before its atoms are pushed
+        custom_res = protor_res = nullptr;
+        if (custom) {
+            auto r = custom->find(resname);
+            if (r != custom->end()) custom_res = &r->second;
+        }
+        auto r = protor_radii().find(resname);
+        if (r != protor_radii().end()) protor_res = &r->second;
+    };
+    auto radius_of = [&](const std::string &atom) -> std::optional<float> {
+        if (custom_res) {
+            auto a = custom_res->find(atom);
+            if (a != custom_res->end()) return a->second;
+        }
+        if (protor_res) {
+            auto a = protor_res->find(atom);
+            if (a != protor_res->end()) return a->second;
+        }
+        return std::nullopt;
+    };
     auto push = [&](const pdb::AtomRec &a, const std::string &resname, const std::string &altloc) {
         if (a.element.empty()) throw SASACalcError(SASACalcError::Kind::ElementMissing, "Element missing for atom");
         if (a.element == "H" && !opt.include_hydrogens) return;
@@ -169,7 +198,7 @@ Packed build_atoms_and_mapping(const pdb::PDB &pdb, LevelKind level, const Optio
         float radius;
         if (opt.read_radii_from_occupancy) {
             radius = (float)a.occupancy;
-        } else if (auto r = get_radius(resname, a.name, custom)) {
+        } else if (auto r = radius_of(a.name)) {
             radius = *r;
         } else if (opt.allow_vdw_fallback) {
             auto it = vdw_radii().find(a.element);
@@ -200,6 +229,7 @@ Packed build_atoms_and_mapping(const pdb::PDB &pdb, LevelKind level, const Optio
                     auto name = residue_name(r);
                     if (r.conformers.empty()) continue;
                     const pdb::Conformer &conf = r.conformers[0];   // first conformer only (src/options.rs:255)
+                    set_residue(*name);
                     for (const pdb::AtomRec &a : conf.atoms) push(a, *name, conf.altloc);
                 }
         return out;
@@ -218,7 +248,9 @@ Packed build_atoms_and_mapping(const pdb::PDB &pdb, LevelKind level, const Optio
                 if (!r.conformers.empty()) {
                     const pdb::Conformer &conf = r.conformers[0];
                     // ProteinLevel hashes ("", serial) for the atom id (src/options.rs:453)
-                    for (const pdb::AtomRec &a : conf.atoms) push(a, *name, level == LevelKind::Protein ? std::string() : conf.altloc);
+                    set_residue(*name);
+                    const std::string no_altloc;
+                    for (const pdb::AtomRec &a : conf.atoms) push(a, *name, level == LevelKind::Protein ? no_altloc : conf.altloc);
                     if (level != LevelKind::Chain) key_range[rkey] = {begin, (std::uint32_t)out.n_atoms()};
                 }
                 if (level != LevelKind::Chain) {
