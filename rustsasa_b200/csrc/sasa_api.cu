@@ -316,15 +316,19 @@ struct sasa_b200_batch {
 
 namespace {
 
-// Queue of the gated single-launch pipeline.  The per-chunk launches work every chunk largest-first, so big structures turn up
-// all the way to the end of the batch; one launch over a chunk-major queue inherits that (measured: 5.21 ms against 5.00 ms for
-// the batch-wide largest-first order of a device-resident run).  But a structure may be queued anywhere after its chunk has
-// arrived, and the copies run ahead of the kernels -- so the queue is built by simulation: work proceeds at one atom per unit of
-// time, chunk c has arrived once kGatedRate x time has passed its last atom, and every position takes the LARGEST structure that
-// has arrived.  After the copies are done (half way through the work at the real copy rate) what is left is in exact
-// largest-first order.  The rate assumed here is deliberately below the real ratio of copy to compute speed (about 2 for the 13-byte
-// wire format): where it is still too optimistic a CTA waits at the gate for a moment, never wrongly.
-constexpr double kGatedRate = 1.25;
+// Queue of the gated single-launch pipeline: CHUNK-MAJOR -- the structures of chunk 0 largest-first, then those of chunk 1, ... --
+// so that a CTA only ever waits for the chunk the copy stream is working on and a slow copy (eight ranks sharing one host, pageable
+// input) degrades the run gracefully: everything that has arrived is worked on, the end is the last chunk's copy plus its work.
+// The builder can also simulate arrival against work and give every position the largest structure that has arrived
+// (SASA_B200_GATED_RATE = assumed ratio of copy to compute speed in atoms, > 0): after the copies are done the rest of the queue
+// is then in exact largest-first order, as in a device-resident run.  Measured on cfg2 with rate 1.25 (the real ratio is about 2
+// for the 13-byte wire format on one GPU): 5.21 -> 5.18 ms.  It is off by default because it is fragile: where the copies are
+// slower than assumed, large structures of chunks still to come sit at the head of the queue, the CTAs wait for them, and the small
+// structures of every chunk pile up behind the last copy.
+static double gated_rate() {
+    static const double r = [] { const char *e = getenv("SASA_B200_GATED_RATE"); return e ? atof(e) : 0.0; }();
+    return r;
+}
 void build_gated_order(sasa_b200_batch *b, int variant) {
     std::vector<uint32_t> &order = b->h_gorder[variant], &need = b->h_gneed[variant];
     order.clear();
@@ -342,6 +346,7 @@ void build_gated_order(sasa_b200_batch *b, int variant) {
     std::vector<uint32_t> chunk_of(b->S, 0);
     size_t next_chunk = 0;
     double t = 0.0;
+    const double rate = gated_rate();
     auto arrive = [&]() {
         const Chunk &ch = plan[next_chunk];
         for (uint32_t i = ch.s0; i < ch.s1; ++i) {
@@ -353,7 +358,7 @@ void build_gated_order(sasa_b200_batch *b, int variant) {
     };
     arrive();
     while (order.size() < b->S) {
-        while (next_chunk < plan.size() && (heap.empty() || (double)(plan[next_chunk].a1 - plan[0].a1) <= kGatedRate * t)) arrive();
+        while (next_chunk < plan.size() && (heap.empty() || (rate > 0.0 && (double)(plan[next_chunk].a1 - plan[0].a1) <= rate * t))) arrive();
         std::pop_heap(heap.begin(), heap.end(), less);
         const std::pair<uint32_t, uint32_t> top = heap.back();
         heap.pop_back();
