@@ -399,7 +399,7 @@ __device__ __forceinline__ void wait_ready(const KParams &p, uint32_t w) {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ready) : "memory");
         if (v >= need) return;
         __nanosleep(200);
-        if (clock64() - t0 > (1ll << 33)) {   // about four seconds
+        if (clock64() - t0 > (1ll << 36)) {   // about half a minute: far beyond any copy, short of a driver time-out
             atomicExch(p.err_flag, 2);
             return;
         }
