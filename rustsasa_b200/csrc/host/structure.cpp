@@ -48,7 +48,7 @@ std::vector<std::string_view> split_ws(std::string_view s) {
 // isspace of the "C" locale, inline (twelve calls per atom record)
 inline bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
-std::string_view trim(std::string_view s) {
+__attribute__((always_inline)) inline std::string_view trim(std::string_view s) {
     while (!s.empty() && is_space(s.front())) s.remove_prefix(1);
     while (!s.empty() && is_space(s.back())) s.remove_suffix(1);
     return s;
@@ -294,13 +294,21 @@ long parse_long(std::string_view s, bool *ok = nullptr) {
     return r.ec == std::errc() ? v : 0;
 }
 
+__attribute__((noinline)) double parse_double_slow(std::string_view s, std::string_view t) {
+    double v = 0.0;
+    const auto r = std::from_chars(t.data(), t.data() + t.size(), v, std::chars_format::general);
+    if (r.ec == std::errc() && r.ptr == t.data() + t.size()) return v;
+    const std::string tmp(s);
+    return std::strtod(tmp.c_str(), nullptr);
+}
+
 double parse_double(std::string_view s) {
     s = trim(s);
     std::string_view t = s;
     if (!t.empty() && t.front() == '+') t.remove_prefix(1);
     {   // fast path for plain decimals (what coordinate, occupancy and B-factor columns hold): an integer mantissa below 2^53
         // over an exact power of ten is ONE correctly rounded division -- the same double a correctly rounded decimal parser
-        // (from_chars below, Rust's str::parse::<f64> in the reference) returns
+        // (from_chars in parse_double_slow, Rust's str::parse::<f64> in the reference) returns
         static const double kPow10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
         const char *q = t.data(), *const end = q + t.size();
         const bool neg = q < end && *q == '-';
@@ -324,11 +332,7 @@ double parse_double(std::string_view s) {
             return neg ? -v : v;
         }
     }
-    double v = 0.0;
-    const auto r = std::from_chars(t.data(), t.data() + t.size(), v, std::chars_format::general);
-    if (r.ec == std::errc() && r.ptr == t.data() + t.size()) return v;
-    const std::string tmp(s);
-    return std::strtod(tmp.c_str(), nullptr);
+    return parse_double_slow(s, t);
 }
 
 void flush_model(PDB &pdb, Model &model) {
@@ -350,10 +354,12 @@ std::string read_file(const std::string &path) {
 }
 
 // Upper-cased, trimmed copy of a short fixed-width field into `out` (no heap: these fit the small-string buffer).
-void upper_trim(std::string_view f, std::string &out) {
+// (the "C" locale's toupper -- the process never sets another -- written out: std::toupper is a call per character)
+__attribute__((always_inline)) inline void upper_trim(std::string_view f, std::string &out) {
     f = trim(f);
     out.assign(f);
-    for (char &c : out) c = (char)std::toupper((unsigned char)c);
+    for (char &c : out)
+        if (c >= 'a' && c <= 'z') c = (char)(c - 'a' + 'A');
 }
 }  // namespace
 
